@@ -1,0 +1,510 @@
+// kernels.cu -- hand-written sm_100a kernels of the surface-multigrid V-cycle.
+//
+// All hot-path matrices are stored SELL-32 (plan.hpp): a slice is 32 consecutive
+// rows, stored column-major inside the slice, so the 32 lanes of a warp (one row
+// each) read 32 consecutive doubles (256 B) + 32 consecutive int32 (128 B) per
+// step: fully coalesced, and the per-row accumulation order is exactly the
+// reference's ascending-index order.  The kernels are HBM-bound (about 0.17
+// flop/byte): no tensor cores, no shared-memory tiling; matrix streams bypass L1
+// (ld.global.nc.L1::no_allocate) so L1 is left to the gathered vector entries.
+//
+// Arithmetic: __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn everywhere on the parity
+// surface, so nvcc never contracts a*b+c into an FMA: the reference is built
+// without FMA (x86-64 baseline, 03_mg_solver/CMakeLists.txt:2,21-24) and bit
+// parity in wavefront mode depends on it.
+#include "kernels.hpp"
+
+namespace smg {
+
+namespace {
+
+constexpr int kBlock = 256;  // threads per CTA = 8 slices
+
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// sum[q] (+)= sum over the row's stored entries of val * x[col + q*ldx], entries in
+// storage order (ascending original index), products and sums rounded separately.
+template <int K, bool SKIP_DIAG>
+__device__ __forceinline__ void row_accumulate(const int* __restrict__ col,
+                                               const double* __restrict__ val, int base, int w,
+                                               int lane, int row, const double* x, int ldx,
+                                               double (&sum)[K]) {
+  const int* cp = col + base + lane;
+  const double* vp = val + base + lane;
+  int j = 0;
+  for (; j + 4 <= w; j += 4) {
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      c[t] = ld_stream_s32(cp + (j + t) * 32);
+      v[t] = ld_stream_f64(vp + (j + t) * 32);
+    }
+    double xv[4][K];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+      for (int q = 0; q < K; q++) xv[t][q] = x[c[t] + (size_t)q * ldx];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        const double s = __dadd_rn(sum[q], __dmul_rn(v[t], xv[t][q]));
+        sum[q] = (SKIP_DIAG && c[t] == row) ? sum[q] : s;
+      }
+  }
+  for (; j < w; j++) {
+    const int c = ld_stream_s32(cp + j * 32);
+    const double v = ld_stream_f64(vp + j * 32);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      const double s = __dadd_rn(sum[q], __dmul_rn(v, x[c + (size_t)q * ldx]));
+      sum[q] = (SKIP_DIAG && c == row) ? sum[q] : s;
+    }
+  }
+}
+
+enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2 };
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kBlock)
+sell_apply_kernel(int nrows, const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                  const double* __restrict__ val, const double* __restrict__ x, int ldx,
+                  const double* __restrict__ b, double* __restrict__ y, int ldy) {
+  const int row = blockIdx.x * kBlock + threadIdx.x;
+  if (row >= nrows) return;
+  const int s = row >> 5, lane = row & 31;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  double sum[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) sum[q] = 0.0;
+  row_accumulate<K, false>(col, val, base, w, lane, row, x, ldx, sum);
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const size_t o = row + (size_t)q * ldy;
+    if (MODE == MODE_SPMV) y[o] = sum[q];
+    if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(b[o], sum[q]);
+    if (MODE == MODE_ADD) y[o] = __dadd_rn(y[o], sum[q]);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+sell_residual_norm_kernel(int nrows, const int* __restrict__ slice_ptr,
+                          const int* __restrict__ col, const double* __restrict__ val,
+                          const double* __restrict__ x, const double* __restrict__ b, int ld,
+                          double* __restrict__ partial) {
+  const int row = blockIdx.x * kBlock + threadIdx.x;
+  double d2 = 0.0;
+  if (row < nrows) {
+    const int s = row >> 5, lane = row & 31;
+    const int base = slice_ptr[s];
+    const int w = (slice_ptr[s + 1] - base) >> 5;
+    double sum[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) sum[q] = 0.0;
+    row_accumulate<K, false>(col, val, base, w, lane, row, x, ld, sum);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      const double d = __dsub_rn(b[row + (size_t)q * ld], sum[q]);
+      d2 += d * d;
+    }
+  }
+  // fixed-shape reduction: warp shuffle tree, then the 8 warp sums in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
+  __shared__ double wsum[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sm[1024];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) t += partial[i];
+  sm[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+// One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
+// independent, so updating them in place and in parallel is exactly the sequential
+// sweep of mg_VCycle.cpp:147-158 restricted to those rows.
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+sell_gs_phase_kernel(int row0, int ps, int pe, const int* __restrict__ slice_ptr,
+                     const int* __restrict__ col, const double* __restrict__ val,
+                     const double* __restrict__ diag, const double* __restrict__ b, double* u,
+                     int ld) {
+  const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
+  if (row < ps || row >= pe) return;
+  const int s = row >> 5, lane = row & 31;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  double sum[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) sum[q] = 0.0;
+  row_accumulate<K, true>(col, val, base, w, lane, row, u, ld, sum);
+  const double d = diag[row];
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const size_t o = row + (size_t)q * ld;
+    u[o] = __ddiv_rn(__dsub_rn(b[o], sum[q]), d);
+  }
+}
+
+inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace
+
+#define SMG_DISPATCH_K(k, ...)                 \
+  switch (k) {                                 \
+    case 1: { constexpr int K = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int K = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int K = 3; __VA_ARGS__; } break; \
+    default: { constexpr int K = 4; __VA_ARGS__; } break; \
+  }
+
+void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
+                 int k, cudaStream_t st) {
+  if (M.nrows <= 0) return;
+  const double* v = use_valT ? M.valT : M.val;
+  const int g = blocks_for(M.nrows, kBlock);
+  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_SPMV><<<g, kBlock, 0, st>>>(
+                        M.nrows, M.slice_ptr, M.col, v, x, ldx, nullptr, y, ldy)));
+}
+
+void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
+                     cudaStream_t st) {
+  if (M.nrows <= 0) return;
+  const int g = blocks_for(M.nrows, kBlock);
+  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_RESIDUAL><<<g, kBlock, 0, st>>>(
+                        M.nrows, M.slice_ptr, M.col, M.valT, x, ld, b, r, ld)));
+}
+
+void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, int ldu, int k,
+                        cudaStream_t st) {
+  if (M.nrows <= 0) return;
+  const int g = blocks_for(M.nrows, kBlock);
+  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_ADD><<<g, kBlock, 0, st>>>(
+                        M.nrows, M.slice_ptr, M.col, M.val, x, ldx, nullptr, u, ldu)));
+}
+
+int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, kBlock); }
+
+void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
+                           double* scratch, double* out, cudaStream_t st) {
+  const int g = residual_norm_blocks(M.nrows);
+  SMG_DISPATCH_K(k, (sell_residual_norm_kernel<K><<<g, kBlock, 0, st>>>(
+                        M.nrows, M.slice_ptr, M.col, M.valT, x, b, ld, scratch)));
+  reduce_partials_kernel<<<1, 1024, 0, st>>>(scratch, g, out);
+}
+
+void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
+                     int k, int ps, int pe, cudaStream_t st) {
+  if (pe <= ps) return;
+  const int row0 = ps & ~31;
+  const int g = blocks_for(pe - row0, kBlock);
+  SMG_DISPATCH_K(k, (sell_gs_phase_kernel<K><<<g, kBlock, 0, st>>>(
+                        row0, ps, pe, M.slice_ptr, M.col, M.val, diag, b, u, ld)));
+}
+
+// ---------------------------------------------------------------------------
+// setup-time numeric kernels
+// ---------------------------------------------------------------------------
+namespace {
+
+__global__ void gather_values_kernel(const double* __restrict__ in, const int* __restrict__ idx,
+                                     double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
+__global__ void fill_sell_kernel(const double* __restrict__ csc, const int* __restrict__ src,
+                                 const int* __restrict__ tmap, double* __restrict__ val,
+                                 double* __restrict__ valT, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = src[i];
+  val[i] = s >= 0 ? csc[s] : 0.0;
+  if (tmap) valT[i] = s >= 0 ? csc[tmap[s]] : 0.0;
+}
+
+__global__ void extract_diag_kernel(const double* __restrict__ csc,
+                                    const int* __restrict__ diag_pos,
+                                    const int* __restrict__ perm, double* __restrict__ diag,
+                                    int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) diag[r] = csc[diag_pos[perm[r]]];
+}
+
+__global__ void shift_diag_kernel(double* csc, const int* __restrict__ diag_pos, int n,
+                                  double shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) csc[diag_pos[i]] = __dadd_rn(csc[diag_pos[i]], shift);
+}
+
+// T1(i,j) = sum_{k in A(:,j), ascending} PT(i,k) * A(k,j), PT(i,k) = P(k,i) looked up
+// in row k of P.  First touch assigns, later touches add (Eigen's conservative
+// product), products and sums rounded separately.
+__global__ void galerkin_t1_kernel(int nnz, const int* __restrict__ t_row,
+                                   const int* __restrict__ t_col,
+                                   const int* __restrict__ a_colptr,
+                                   const int* __restrict__ a_rowidx,
+                                   const double* __restrict__ a_val,
+                                   const int* __restrict__ prow_ptr,
+                                   const int* __restrict__ pcol, const double* __restrict__ pval,
+                                   double* __restrict__ t_val) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int i = t_row[e], j = t_col[e];
+  double acc = 0.0;
+  bool first = true;
+  for (int p = a_colptr[j]; p < a_colptr[j + 1]; p++) {
+    const int k = a_rowidx[p];
+    for (int q = prow_ptr[k]; q < prow_ptr[k + 1]; q++)
+      if (pcol[q] == i) {
+        const double t = __dmul_rn(pval[q], a_val[p]);
+        acc = first ? t : __dadd_rn(acc, t);
+        first = false;
+        break;
+      }
+  }
+  t_val[e] = acc;
+}
+
+// Ac(i,j) = sum_{k in P(:,j), ascending} T1(i,k) * P(k,j)
+__global__ void galerkin_ac_kernel(int nnz, const int* __restrict__ c_row,
+                                   const int* __restrict__ c_col,
+                                   const int* __restrict__ p_colptr,
+                                   const int* __restrict__ p_rowidx,
+                                   const double* __restrict__ p_val,
+                                   const int* __restrict__ t_colptr,
+                                   const int* __restrict__ t_rowidx,
+                                   const double* __restrict__ t_val,
+                                   double* __restrict__ c_val) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int i = c_row[e], j = c_col[e];
+  double acc = 0.0;
+  bool first = true;
+  for (int p = p_colptr[j]; p < p_colptr[j + 1]; p++) {
+    const int k = p_rowidx[p];
+    int lo = t_colptr[k], hi = t_colptr[k + 1];
+    while (lo < hi) {  // binary search for row i in column k of T1
+      const int mid = (lo + hi) >> 1;
+      if (t_rowidx[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    if (lo < t_colptr[k + 1] && t_rowidx[lo] == i) {
+      const double t = __dmul_rn(t_val[lo], p_val[p]);
+      acc = first ? t : __dadd_rn(acc, t);
+      first = false;
+    }
+  }
+  c_val[e] = acc;
+}
+
+__global__ void csc_to_dense_kernel(int nnz, const int* __restrict__ rowidx,
+                                    const int* __restrict__ colidx,
+                                    const double* __restrict__ val,
+                                    const int* __restrict__ iperm, double* __restrict__ D,
+                                    int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  D[(size_t)iperm[rowidx[e]] + (size_t)iperm[colidx[e]] * n] = val[e];
+}
+
+__global__ void symmetrize_lower_kernel(double* D, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < n && c < n && r > c) D[(size_t)c + (size_t)r * n] = D[(size_t)r + (size_t)c * n];
+}
+
+// u(i,:) += sum_j Ainv(i,j) b(j,:) ; one warp per row, Ainv symmetric so row i is
+// read as the contiguous column i.
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+dense_symv_add_kernel(const double* __restrict__ Ainv, const double* __restrict__ b, double* u,
+                      int n) {
+  const int i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const double* a = Ainv + (size_t)i * n;
+  double acc[K];
+#pragma unroll
+  for (int q = 0; q < K; q++) acc[q] = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const double aij = ld_stream_f64(a + j);
+#pragma unroll
+    for (int q = 0; q < K; q++) acc[q] += aij * b[j + (size_t)q * n];
+  }
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) u[i + (size_t)q * n] = u[i + (size_t)q * n] + acc[q];
+  }
+}
+
+__global__ void gather_system_kernel(const double* __restrict__ RHS,
+                                     const double* __restrict__ z0,
+                                     const double* __restrict__ kv, int n_full, int n_known,
+                                     const int* __restrict__ g, const int* __restrict__ auk_ptr,
+                                     const int* __restrict__ auk_q,
+                                     const double* __restrict__ auk_val, double* __restrict__ bu,
+                                     double* __restrict__ zu, int nu, int k) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nu) return;
+  const int src = g[r];
+  for (int q = 0; q < k; q++) {
+    zu[r + (size_t)q * nu] = z0[src + (size_t)q * n_full];
+    double rhs = RHS[src + (size_t)q * n_full];
+    if (auk_ptr) {
+      // RHS_unknown - (Auk * known_val): the product accumulates from zero in
+      // ascending known-column order (cpp:316-318)
+      double t = 0.0;
+      for (int p = auk_ptr[r]; p < auk_ptr[r + 1]; p++)
+        t = __dadd_rn(t, __dmul_rn(auk_val[p], kv[auk_q[p] + (size_t)q * n_known]));
+      rhs = __dsub_rn(rhs, t);
+    }
+    bu[r + (size_t)q * nu] = rhs;
+  }
+}
+
+__global__ void scatter_solution_kernel(const double* __restrict__ zu, const int* __restrict__ g,
+                                        double* __restrict__ z, int n_full, int nu, int k) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nu) return;
+  const int dst = g[r];
+  for (int q = 0; q < k; q++) z[dst + (size_t)q * n_full] = zu[r + (size_t)q * nu];
+}
+
+__global__ void scatter_known_kernel(const double* __restrict__ kv, const int* __restrict__ kidx,
+                                     const int* __restrict__ ksrc, double* __restrict__ z,
+                                     int n_full, int n_known, int n_distinct, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_distinct) return;
+  for (int q = 0; q < k; q++)
+    z[kidx[i] + (size_t)q * n_full] = kv[ksrc[i] + (size_t)q * n_known];
+}
+
+__global__ void permute_in_kernel(const double* __restrict__ in, const int* __restrict__ perm,
+                                  double* __restrict__ out, int n, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = perm[i];
+  for (int q = 0; q < k; q++) out[i + (size_t)q * n] = in[s + (size_t)q * n];
+}
+
+__global__ void permute_out_kernel(const double* __restrict__ in, const int* __restrict__ perm,
+                                   double* __restrict__ out, int n, int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = perm[i];
+  for (int q = 0; q < k; q++) out[d + (size_t)q * n] = in[i + (size_t)q * n];
+}
+
+__global__ void fill_kernel(double* p, double v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+void launch_gather_values(const double* in, const int* idx, double* out, int n, cudaStream_t st) {
+  if (n > 0) gather_values_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, idx, out, n);
+}
+void launch_fill_sell(const double* csc, const int* src, const int* tmap, double* val,
+                      double* valT, int64_t n, cudaStream_t st) {
+  if (n > 0) fill_sell_kernel<<<blocks_for(n, 256), 256, 0, st>>>(csc, src, tmap, val, valT, n);
+}
+void launch_extract_diag(const double* csc, const int* diag_pos, const int* perm, double* diag,
+                         int n, cudaStream_t st) {
+  if (n > 0) extract_diag_kernel<<<blocks_for(n, 256), 256, 0, st>>>(csc, diag_pos, perm, diag, n);
+}
+void launch_shift_diag(double* csc, const int* diag_pos, int n, double shift, cudaStream_t st) {
+  if (n > 0) shift_diag_kernel<<<blocks_for(n, 256), 256, 0, st>>>(csc, diag_pos, n, shift);
+}
+void launch_galerkin_t1(int nnz_t1, const int* t_row, const int* t_col, const int* a_colptr,
+                        const int* a_rowidx, const double* a_val, const int* prow_ptr,
+                        const int* pcol, const double* pval, double* t_val, cudaStream_t st) {
+  if (nnz_t1 > 0)
+    galerkin_t1_kernel<<<blocks_for(nnz_t1, 256), 256, 0, st>>>(
+        nnz_t1, t_row, t_col, a_colptr, a_rowidx, a_val, prow_ptr, pcol, pval, t_val);
+}
+void launch_galerkin_ac(int nnz_ac, const int* c_row, const int* c_col, const int* p_colptr,
+                        const int* p_rowidx, const double* p_val, const int* t_colptr,
+                        const int* t_rowidx, const double* t_val, double* c_val,
+                        cudaStream_t st) {
+  if (nnz_ac > 0)
+    galerkin_ac_kernel<<<blocks_for(nnz_ac, 256), 256, 0, st>>>(
+        nnz_ac, c_row, c_col, p_colptr, p_rowidx, p_val, t_colptr, t_rowidx, t_val, c_val);
+}
+void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const double* val,
+                         const int* iperm, double* D, int n, cudaStream_t st) {
+  if (nnz > 0)
+    csc_to_dense_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, rowidx, colidx, val, iperm, D, n);
+}
+void launch_symmetrize_lower(double* D, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8);
+  symmetrize_lower_kernel<<<g, b, 0, st>>>(D, n);
+}
+void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
+                           cudaStream_t st) {
+  if (n <= 0) return;
+  const int g = blocks_for(n, kBlock / 32);
+  SMG_DISPATCH_K(k, (dense_symv_add_kernel<K><<<g, kBlock, 0, st>>>(Ainv, b, u, n)));
+}
+void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
+                          int n_known, const int* g, const int* auk_ptr, const int* auk_q,
+                          const double* auk_val, double* bu, double* zu, int nu, int k,
+                          cudaStream_t st) {
+  if (nu > 0)
+    gather_system_kernel<<<blocks_for(nu, 256), 256, 0, st>>>(
+        RHS, z0, kv, n_full, n_known, g, auk_ptr, auk_q, auk_val, bu, zu, nu, k);
+}
+void launch_scatter_solution(const double* zu, const int* g, double* z, int n_full, int nu, int k,
+                             cudaStream_t st) {
+  if (nu > 0) scatter_solution_kernel<<<blocks_for(nu, 256), 256, 0, st>>>(zu, g, z, n_full, nu, k);
+}
+void launch_scatter_known(const double* kv, const int* kidx, const int* ksrc, double* z,
+                          int n_full, int n_known, int n_distinct, int k, cudaStream_t st) {
+  if (n_distinct > 0)
+    scatter_known_kernel<<<blocks_for(n_distinct, 256), 256, 0, st>>>(kv, kidx, ksrc, z, n_full,
+                                                                     n_known, n_distinct, k);
+}
+void launch_permute_in(const double* in, const int* perm, double* out, int n, int k,
+                       cudaStream_t st) {
+  if (n > 0) permute_in_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
+}
+void launch_permute_out(const double* in, const int* perm, double* out, int n, int k,
+                        cudaStream_t st) {
+  if (n > 0) permute_out_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
+}
+void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
+  if (n > 0) fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, v, n);
+}
+
+}  // namespace smg

@@ -1,0 +1,92 @@
+// kernels.hpp -- launch wrappers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace smg {
+
+// Device view of a SELL-32 matrix (see plan.hpp::Sell). `val` holds, for row i,
+// the entries of CSC column i (what the reference's smoother reads); `valT` holds
+// the true row i (entries A(i,j)), which is what A*x needs. For exactly symmetric
+// matrices the two arrays have identical contents.
+struct SellDev {
+  int nrows = 0;
+  int nslices = 0;
+  const int* slice_ptr = nullptr;
+  const int* col = nullptr;
+  const double* val = nullptr;
+  const double* valT = nullptr;
+};
+
+constexpr int kMaxK = 4;  // right-hand sides handled per kernel pass
+
+// y = M x  (y: nrows x k, ldy; x: ldx)
+void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
+                 int k, cudaStream_t st);
+// r = b - M x
+void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
+                     cudaStream_t st);
+// u = u + M x   (u: nrows x k, ldu; x: ldx)
+void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, int ldu, int k,
+                        cudaStream_t st);
+// *out = || b - M x ||_F^2, deterministic; scratch must hold >= residual_norm_blocks(nrows) doubles
+int residual_norm_blocks(int nrows);
+void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
+                           double* scratch, double* out, cudaStream_t st);
+// one Gauss-Seidel phase: rows [ps, pe) of the permuted matrix, in place on u
+void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
+                     int k, int ps, int pe, cudaStream_t st);
+
+// ---- setup-time numeric kernels ---------------------------------------------
+// out[i] = in[idx[i]]
+void launch_gather_values(const double* in, const int* idx, double* out, int n, cudaStream_t st);
+// SELL values from CSC values: val[s] = src[s] >= 0 ? csc[src[s]] : 0 ;
+// valT[s] = src[s] >= 0 ? csc[tmap[src[s]]] : 0 (tmap may be null: valT not written)
+void launch_fill_sell(const double* csc, const int* src, const int* tmap, double* val,
+                      double* valT, int64_t n, cudaStream_t st);
+// diag[r] = csc[diag_pos[perm[r]]]
+void launch_extract_diag(const double* csc, const int* diag_pos, const int* perm, double* diag,
+                         int n, cudaStream_t st);
+// csc[diag_pos[i]] += shift
+void launch_shift_diag(double* csc, const int* diag_pos, int n, double shift, cudaStream_t st);
+// T1 = PT * A (values): thread per T1 entry.
+//   t_row/t_col: entry coordinates (coarse i, fine j); A: CSC of the fine matrix;
+//   P by fine row: prow_ptr/pcol/pval (= CSC arrays of PT)
+void launch_galerkin_t1(int nnz_t1, const int* t_row, const int* t_col, const int* a_colptr,
+                        const int* a_rowidx, const double* a_val, const int* prow_ptr,
+                        const int* pcol, const double* pval, double* t_val, cudaStream_t st);
+// Ac = T1 * P (values): thread per Ac entry (i, j).
+void launch_galerkin_ac(int nnz_ac, const int* c_row, const int* c_col, const int* p_colptr,
+                        const int* p_rowidx, const double* p_val, const int* t_colptr,
+                        const int* t_rowidx, const double* t_val, double* c_val,
+                        cudaStream_t st);
+// dense (permuted) copy of a CSC matrix: D[iperm[r] + iperm[c]*n] = val
+void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const double* val,
+                         const int* iperm, double* D, int n, cudaStream_t st);
+// mirror the lower triangle of a column-major n x n matrix into the upper one
+void launch_symmetrize_lower(double* D, int n, cudaStream_t st);
+// u = u + Ainv * b  (Ainv symmetric dense n x n; b,u: n x k)
+void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
+                           cudaStream_t st);
+
+// ---- solve-time gather / scatter ----------------------------------------------
+// zu[r] = z0[g[r]] ; bu[r] = RHS[g[r]] - sum_q Auk(row r, q) kv[q]   (per column)
+void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
+                          int n_known, const int* g, const int* auk_ptr, const int* auk_q,
+                          const double* auk_val, double* bu, double* zu, int nu, int k,
+                          cudaStream_t st);
+// z[g[r]] = zu[r]
+void launch_scatter_solution(const double* zu, const int* g, double* z, int n_full, int nu, int k,
+                             cudaStream_t st);
+// z[kidx[i]] = kv[ksrc[i]]  (distinct kidx; ksrc = last occurrence in `known`)
+void launch_scatter_known(const double* kv, const int* kidx, const int* ksrc, double* z,
+                          int n_full, int n_known, int n_distinct, int k, cudaStream_t st);
+// out[i] = in[perm[i]] per column (perm: new->old)  /  out[perm[i]] = in[i]
+void launch_permute_in(const double* in, const int* perm, double* out, int n, int k,
+                       cudaStream_t st);
+void launch_permute_out(const double* in, const int* perm, double* out, int n, int k,
+                        cudaStream_t st);
+void launch_fill(double* p, double v, int64_t n, cudaStream_t st);
+
+}  // namespace smg

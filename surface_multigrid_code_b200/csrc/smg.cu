@@ -1,0 +1,1199 @@
+// smg.cu -- the C ABI of libsmg.so (include/smg.h): handle, device residency of the
+// multigrid hierarchy, min_quad_with_fixed_mg_precompute / _solve and the mg_VCycle
+// operators, driven by the sm_100a kernels of kernels.cu.
+//
+// Reference behaviour replaced (file:line under the reference tree):
+//   src/min_quad_with_fixed_mg.cpp:3-51, :137-257   precompute  -> smg_precompute
+//   src/min_quad_with_fixed_mg.cpp:80-135, :288-361 solve       -> smg_solve[_device]
+//   src/mg_VCycle.cpp:3-59                           mg_VCycle   -> smg_vcycle / vcycle_device
+//   src/mg_VCycle.cpp:62-92, :113-201                A/restrict/prolong/relax/coarseSolve
+//
+// Data layout in HBM (per level l, n_l rows, everything FP64 / int32):
+//   * rows are renumbered phase-major (smoother colour or wavefront level first, then
+//     a breadth-first locality rank, then descending row length inside sigma windows);
+//     all level vectors (b, u, r; n_l x k column-major) live in that numbering;
+//   * A_l   : SELL-32 (col, val = column-i-as-row-i, valT = true row i), plus its CSC
+//             value array in reference order (Galerkin input / parity read-back);
+//   * P_l   : SELL-32 by fine row (columns in level l's numbering), PT_l: SELL-32 by
+//             coarse row (columns in level l-1's numbering);
+//   * coarsest level: dense symmetric inverse (n_c x n_c) for the direct solve.
+// There is no CPU compute path in this file: without a CUDA device every compute
+// entry point fails with SMG_E_CUDA / SMG_E_STATE.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/smg.h"
+#include "kernels.hpp"
+#include "plan.hpp"
+
+namespace {
+
+using smg::Csc;
+using smg::SellDev;
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- device buffers ----------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; o.p = nullptr; o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    else p = nullptr;
+    return e;
+  }
+  cudaError_t reserve(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t st) {
+    cudaError_t e = alloc(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+};
+
+struct SellBufs {
+  DevBuf<int> slice_ptr, col, src;
+  DevBuf<double> val, valT;
+  int nrows = 0, nslices = 0;
+  int64_t padded = 0;
+  SellDev view() const {
+    SellDev d;
+    d.nrows = nrows;
+    d.nslices = nslices;
+    d.slice_ptr = slice_ptr.p;
+    d.col = col.p;
+    d.val = val.p;
+    d.valT = valT.p ? valT.p : val.p;
+    return d;
+  }
+};
+
+struct LevelDev {
+  int n = 0;
+  // CSC of mg[l].A in reference order (pattern static, values numeric)
+  DevBuf<int> a_colptr, a_rowidx, a_col, tmap, diag_pos;
+  DevBuf<double> a_val;
+  SellBufs sellA;
+  DevBuf<double> diag;  // permuted numbering
+  DevBuf<int> perm;     // new -> old
+  std::vector<int> phase_ptr;
+  // transfer operators between level l-1 (fine) and l (coarse), l >= 1
+  SellBufs sellP, sellPT;
+  DevBuf<int> p_colptr, p_rowidx, pt_colptr, pt_rowidx;  // CSC of P and of PT
+  DevBuf<double> p_val, pt_val;
+  DevBuf<int> t_colptr, t_rowidx, t_col;  // T1 = PT * A_{l-1}
+  DevBuf<double> t_val;
+  // work vectors (permuted numbering), n x kcap column-major, ld = n
+  DevBuf<double> b, u, r;
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
+
+}  // namespace
+
+struct smg_handle {
+  smg_options opt;
+  bool plan_only = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  std::string err;
+
+  bool have_hierarchy = false, have_plan = false;
+  std::vector<int> n_rows;
+  std::vector<Csc> P_full;
+  smg::Plan plan;
+  std::vector<LevelDev> lv;
+  int kcap = 0;
+
+  // system gather / scatter
+  DevBuf<double> a_in;  // caller's A values
+  DevBuf<int> lhs_src, auk_src;
+  DevBuf<int> g;                          // permuted unknown row -> caller index
+  DevBuf<int> auk_ptr, auk_q, auk_pos;    // Auk by permuted row; auk_pos -> entry of Auk CSC
+  DevBuf<double> auk_csc_val, auk_val;
+  DevBuf<int> kidx, ksrc;
+  int n_known_distinct = 0;
+
+  // coarse direct solve
+  DevBuf<double> ainv;
+  DevBuf<double> potrf_work;
+  DevBuf<int> dev_info;
+
+  // staging
+  DevBuf<double> st_a, st_b, st_c, st_d;
+  DevBuf<double> norm_scratch, norm_out;
+  double* h_norm = nullptr;  // pinned
+  DevBuf<double> flush;      // L2 flush buffer for smg_time_kernel
+
+  std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+  int64_t launches = 0;
+  double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(smg_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define SMG_CUDA(h, call)                                                          \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess)                                                        \
+      return fail(h, SMG_E_CUDA,                                                   \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));            \
+  } while (0)
+
+#define SMG_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != SMG_OK) return rc__; \
+  } while (0)
+
+int check_launch(smg_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, SMG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return SMG_OK;
+}
+
+void drop_graphs(smg_handle* h) {
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
+int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT) {
+  out->nrows = S.nrows;
+  out->nslices = S.nslices;
+  out->padded = S.padded();
+  SMG_CUDA(h, out->slice_ptr.upload(S.slice_ptr, h->stream));
+  SMG_CUDA(h, out->col.upload(S.col, h->stream));
+  SMG_CUDA(h, out->src.upload(S.src, h->stream));
+  SMG_CUDA(h, out->val.alloc(static_cast<size_t>(S.padded())));
+  if (need_valT) SMG_CUDA(h, out->valT.alloc(static_cast<size_t>(S.padded())));
+  else out->valT.release();
+  return SMG_OK;
+}
+
+int ensure_k(smg_handle* h, int k) {
+  if (k <= h->kcap) return SMG_OK;
+  drop_graphs(h);
+  for (auto& L : h->lv) {
+    const size_t cnt = static_cast<size_t>(L.n) * k;
+    SMG_CUDA(h, L.b.alloc(cnt));
+    SMG_CUDA(h, L.u.alloc(cnt));
+    SMG_CUDA(h, L.r.alloc(cnt));
+  }
+  h->kcap = k;
+  return SMG_OK;
+}
+
+// ---- device-side operators on the level work vectors ---------------------------
+void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, int k) {
+  LevelDev& L = h->lv[l];
+  const SellDev A = L.sellA.view();
+  const int np = static_cast<int>(L.phase_ptr.size()) - 1;
+  for (int it = 0; it < iters; it++)
+    for (int p = 0; p < np; p++)
+      for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+        const int kk = std::min(smg::kMaxK, k - k0);
+        smg::launch_gs_phase(A, L.diag.p, b + static_cast<size_t>(k0) * L.n,
+                             u + static_cast<size_t>(k0) * L.n, L.n, kk, L.phase_ptr[p],
+                             L.phase_ptr[p + 1], h->stream);
+        if (L.phase_ptr[p + 1] > L.phase_ptr[p]) h->launches++;
+      }
+}
+
+void residual_device(smg_handle* h, int l, const double* b, const double* u, double* r, int k) {
+  LevelDev& L = h->lv[l];
+  if (L.n <= 0) return;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    const size_t o = static_cast<size_t>(k0) * L.n;
+    smg::launch_residual(L.sellA.view(), b + o, u + o, r + o, L.n, kk, h->stream);
+    h->launches++;
+  }
+}
+
+void apply_A_device(smg_handle* h, int l, const double* u, double* y, int k) {
+  LevelDev& L = h->lv[l];
+  if (L.n <= 0) return;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    const size_t o = static_cast<size_t>(k0) * L.n;
+    smg::launch_spmv(L.sellA.view(), true, u + o, L.n, y + o, L.n, kk, h->stream);
+    h->launches++;
+  }
+}
+
+// x on level l (fine), y on level l+1
+void restrict_device(smg_handle* h, int l, const double* x, double* y, int k) {
+  LevelDev& F = h->lv[l];
+  LevelDev& C = h->lv[l + 1];
+  if (C.n <= 0) return;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    smg::launch_spmv(C.sellPT.view(), false, x + static_cast<size_t>(k0) * F.n, F.n,
+                     y + static_cast<size_t>(k0) * C.n, C.n, kk, h->stream);
+    h->launches++;
+  }
+}
+
+// y (level l) = P x (level l+1)   /   u (level l) += P x
+void prolong_device(smg_handle* h, int l, const double* x, double* y, int k, bool add) {
+  LevelDev& F = h->lv[l];
+  LevelDev& C = h->lv[l + 1];
+  if (F.n <= 0) return;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    const double* xx = x + static_cast<size_t>(k0) * C.n;
+    double* yy = y + static_cast<size_t>(k0) * F.n;
+    if (add) smg::launch_prolong_add(C.sellP.view(), xx, C.n, yy, F.n, kk, h->stream);
+    else smg::launch_spmv(C.sellP.view(), false, xx, C.n, yy, F.n, kk, h->stream);
+    h->launches++;
+  }
+}
+
+void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
+  LevelDev& L = h->lv.back();
+  if (L.n <= 0) return;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    const size_t o = static_cast<size_t>(k0) * L.n;
+    smg::launch_dense_symv_add(h->ainv.p, b + o, u + o, L.n, kk, h->stream);
+    h->launches++;
+  }
+}
+
+void fill_device(smg_handle* h, double* p, double v, int64_t n) {
+  if (n <= 0) return;
+  smg::launch_fill(p, v, n, h->stream);
+  h->launches++;
+}
+
+// mg_VCycle (src/mg_VCycle.cpp:3-59) unrolled over levels; operates on the resident
+// work vectors lv[l].b / .u of levels l >= lv0.
+void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
+  const int last = static_cast<int>(h->lv.size()) - 1;
+  for (int l = lv0; l < last; l++) {
+    LevelDev& L = h->lv[l];
+    LevelDev& C = h->lv[l + 1];
+    relax_device(h, l, pre, L.b.p, L.u.p, k);              // :36
+    residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
+    restrict_device(h, l, L.r.p, C.b.p, k);                // :44
+    fill_device(h, C.u.p, 0.0, static_cast<int64_t>(C.n) * k);  // :46-47
+  }
+  coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
+  for (int l = last - 1; l >= lv0; l--) {
+    LevelDev& L = h->lv[l];
+    prolong_device(h, l, h->lv[l + 1].u.p, L.u.p, k, true);  // :52-53
+    relax_device(h, l, post, L.b.p, L.u.p, k);               // :56
+  }
+}
+
+int vcycle_run(smg_handle* h, int lv0, int pre, int post, int k) {
+  if (!h->opt.use_graph) {
+    vcycle_device(h, lv0, pre, post, k);
+    return check_launch(h, "vcycle");
+  }
+  const auto key = std::make_tuple(lv0, pre, post, k);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    GraphEntry ge;
+    cudaGraph_t graph = nullptr;
+    const int64_t before = h->launches;
+    SMG_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    vcycle_device(h, lv0, pre, post, k);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    ge.launches = h->launches - before;
+    h->launches = before;
+    if (e != cudaSuccess) return fail(h, SMG_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(h, SMG_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    it = h->graphs.emplace(key, ge).first;
+  }
+  SMG_CUDA(h, cudaGraphLaunch(it->second.exec, h->stream));
+  h->launches += it->second.launches;
+  return SMG_OK;
+}
+
+int residual_norm_device(smg_handle* h, int l, const double* b, const double* u, int k,
+                         double* out_host) {
+  LevelDev& L = h->lv[l];
+  const int nb = smg::residual_norm_blocks(L.n);
+  const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
+  SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(nb)));
+  SMG_CUDA(h, h->norm_out.reserve(static_cast<size_t>(std::max(nchunks, 1))));
+  if (L.n <= 0) {
+    *out_host = 0.0;
+    return SMG_OK;
+  }
+  for (int c = 0; c < nchunks; c++) {
+    const int k0 = c * smg::kMaxK;
+    const int kk = std::min(smg::kMaxK, k - k0);
+    const size_t o = static_cast<size_t>(k0) * L.n;
+    smg::launch_residual_norm2(L.sellA.view(), b + o, u + o, L.n, kk, h->norm_scratch.p,
+                               h->norm_out.p + c, h->stream);
+    h->launches += 2;
+  }
+  SMG_CUDA(h, cudaMemcpyAsync(h->h_norm, h->norm_out.p, sizeof(double) * nchunks,
+                              cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  double ss = 0.0;
+  for (int c = 0; c < nchunks; c++) ss += h->h_norm[c];
+  *out_host = std::sqrt(ss);
+  return SMG_OK;
+}
+
+// ---- numeric part of precompute (device) -----------------------------------------
+int numeric_setup(smg_handle* h) {
+  smg::Plan& pl = h->plan;
+  const int nlev = static_cast<int>(h->lv.size());
+  cudaStream_t st = h->stream;
+  // LHS = A(unknown,unknown), Auk = A(unknown,known): value gathers (cpp:167,170)
+  LevelDev& L0 = h->lv[0];
+  smg::launch_gather_values(h->a_in.p, h->lhs_src.p, L0.a_val.p, pl.LHS.nnz(), st);
+  h->launches++;
+  if (pl.has_fixed && pl.Auk.nnz() > 0) {
+    smg::launch_gather_values(h->a_in.p, h->auk_src.p, h->auk_csc_val.p, pl.Auk.nnz(), st);
+    smg::launch_gather_values(h->auk_csc_val.p, h->auk_pos.p, h->auk_val.p, pl.Auk.nnz(), st);
+    h->launches += 2;
+  }
+  // Galerkin products A_l = (PT * A_{l-1}) * P (cpp:25, :227)
+  for (int l = 1; l < nlev; l++) {
+    LevelDev& F = h->lv[l - 1];
+    LevelDev& C = h->lv[l];
+    const smg::LevelPlan& P = pl.lv[l];
+    smg::launch_galerkin_t1(P.T1.nnz(), C.t_rowidx.p, C.t_col.p, F.a_colptr.p, F.a_rowidx.p,
+                            F.a_val.p, C.pt_colptr.p, C.pt_rowidx.p, C.pt_val.p, C.t_val.p, st);
+    smg::launch_galerkin_ac(P.A.nnz(), C.a_rowidx.p, C.a_col.p, C.p_colptr.p, C.p_rowidx.p,
+                            C.p_val.p, C.t_colptr.p, C.t_rowidx.p, C.t_val.p, C.a_val.p, st);
+    h->launches += 2;
+  }
+  // coarsest diagonal shift (cpp:31-36, :237-242)
+  LevelDev& Lc = h->lv[nlev - 1];
+  smg::launch_shift_diag(Lc.a_val.p, Lc.diag_pos.p, Lc.n, 1e-12, st);
+  h->launches++;
+  // SELL values + A_diag (cpp:38-41, :244-246)
+  for (int l = 0; l < nlev; l++) {
+    LevelDev& L = h->lv[l];
+    smg::launch_fill_sell(L.a_val.p, L.sellA.src.p, L.tmap.p, L.sellA.val.p, L.sellA.valT.p,
+                          L.sellA.padded, st);
+    smg::launch_extract_diag(L.a_val.p, L.diag_pos.p, L.perm.p, L.diag.p, L.n, st);
+    h->launches += 2;
+  }
+  SMG_TRY(check_launch(h, "numeric setup"));
+  // coarse factorisation (cpp:46-48, :253-254): dense Cholesky, explicit inverse
+  const int nc = Lc.n;
+  if (nc > 0) {
+    SMG_CUDA(h, h->ainv.reserve(static_cast<size_t>(nc) * nc));
+    SMG_CUDA(h, cudaMemsetAsync(h->ainv.p, 0, sizeof(double) * nc * nc, st));
+    // natural (reference) numbering -> permuted numbering of the coarsest level
+    std::vector<int>& iperm = pl.lv[nlev - 1].order.iperm;
+    DevBuf<int> d_iperm;
+    SMG_CUDA(h, d_iperm.upload(iperm, st));
+    smg::launch_csc_to_dense(pl.lv[nlev - 1].A.nnz(), Lc.a_rowidx.p, Lc.a_col.p, Lc.a_val.p,
+                             d_iperm.p, h->ainv.p, nc, st);
+    h->launches++;
+    int lwork1 = 0, lwork2 = 0;
+    if (cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
+                                    &lwork1) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
+                                    &lwork2) != CUSOLVER_STATUS_SUCCESS)
+      return fail(h, SMG_E_CUSOLVER, "cusolver bufferSize failed");
+    SMG_CUDA(h, h->potrf_work.reserve(static_cast<size_t>(std::max(lwork1, lwork2))));
+    SMG_CUDA(h, h->dev_info.reserve(2));
+    if (cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
+                         h->potrf_work.p, lwork1, h->dev_info.p) != CUSOLVER_STATUS_SUCCESS)
+      return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotrf failed");
+    if (cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
+                         h->potrf_work.p, lwork2, h->dev_info.p + 1) != CUSOLVER_STATUS_SUCCESS)
+      return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotri failed");
+    int info[2] = {0, 0};
+    SMG_CUDA(h, cudaMemcpyAsync(info, h->dev_info.p, sizeof(info), cudaMemcpyDeviceToHost, st));
+    SMG_CUDA(h, cudaStreamSynchronize(st));
+    if (info[0] != 0 || info[1] != 0)
+      return fail(h, SMG_E_CUSOLVER,
+                  "coarsest matrix is not positive definite (potrf info " +
+                      std::to_string(info[0]) + ", potri info " + std::to_string(info[1]) + ")");
+    smg::launch_symmetrize_lower(h->ainv.p, nc, st);
+    h->launches++;
+    SMG_TRY(check_launch(h, "coarse inverse"));
+  }
+  SMG_CUDA(h, cudaStreamSynchronize(st));
+  return SMG_OK;
+}
+
+int upload_plan(smg_handle* h) {
+  smg::Plan& pl = h->plan;
+  const int nlev = static_cast<int>(pl.lv.size());
+  cudaStream_t st = h->stream;
+  drop_graphs(h);
+  h->lv.clear();
+  h->lv.resize(nlev);
+  h->kcap = 0;
+  for (int l = 0; l < nlev; l++) {
+    smg::LevelPlan& P = pl.lv[l];
+    LevelDev& L = h->lv[l];
+    L.n = P.n;
+    SMG_CUDA(h, L.a_colptr.upload(P.A.colptr, st));
+    SMG_CUDA(h, L.a_rowidx.upload(P.A.rowidx, st));
+    SMG_CUDA(h, L.a_col.upload(P.a_col, st));
+    SMG_CUDA(h, L.tmap.upload(P.tmap, st));
+    SMG_CUDA(h, L.diag_pos.upload(P.diag_pos, st));
+    SMG_CUDA(h, L.a_val.alloc(static_cast<size_t>(P.A.nnz())));
+    SMG_TRY(upload_sell(h, P.sellA, &L.sellA, true));
+    SMG_CUDA(h, L.diag.alloc(static_cast<size_t>(P.n)));
+    SMG_CUDA(h, L.perm.upload(P.order.perm, st));
+    L.phase_ptr = P.order.phase_ptr;
+    if (l >= 1) {
+      SMG_TRY(upload_sell(h, P.sellP, &L.sellP, false));
+      SMG_TRY(upload_sell(h, P.sellPT, &L.sellPT, false));
+      SMG_CUDA(h, L.p_colptr.upload(P.P.colptr, st));
+      SMG_CUDA(h, L.p_rowidx.upload(P.P.rowidx, st));
+      SMG_CUDA(h, L.p_val.upload(P.P.val, st));
+      SMG_CUDA(h, L.pt_colptr.upload(P.PT.colptr, st));
+      SMG_CUDA(h, L.pt_rowidx.upload(P.PT.rowidx, st));
+      SMG_CUDA(h, L.pt_val.upload(P.PT.val, st));
+      SMG_CUDA(h, L.t_colptr.upload(P.T1.colptr, st));
+      SMG_CUDA(h, L.t_rowidx.upload(P.T1.rowidx, st));
+      SMG_CUDA(h, L.t_col.upload(P.t1_col, st));
+      SMG_CUDA(h, L.t_val.alloc(static_cast<size_t>(P.T1.nnz())));
+      // values of the transfer operators are static: fill the SELL arrays now.
+      // sellP was built from PT's CSC, sellPT from P's CSC (plan.cpp).
+      smg::launch_fill_sell(L.pt_val.p, L.sellP.src.p, nullptr, L.sellP.val.p, nullptr,
+                            L.sellP.padded, st);
+      smg::launch_fill_sell(L.p_val.p, L.sellPT.src.p, nullptr, L.sellPT.val.p, nullptr,
+                            L.sellPT.padded, st);
+      h->launches += 2;
+    }
+  }
+  SMG_CUDA(h, h->lhs_src.upload(pl.lhs_src, st));
+  // permuted unknown row -> caller index
+  const std::vector<int>& perm0 = pl.lv[0].order.perm;
+  const int nu = pl.lv[0].n;
+  std::vector<int> g(nu);
+  for (int r = 0; r < nu; r++) g[r] = pl.unknown[perm0[r]];
+  SMG_CUDA(h, h->g.upload(g, st));
+  h->auk_ptr.release();
+  h->n_known_distinct = 0;
+  if (pl.has_fixed) {
+    const Csc& K = pl.Auk;
+    const int nk = K.cols;
+    SMG_CUDA(h, h->auk_src.upload(pl.auk_src, st));
+    SMG_CUDA(h, h->auk_csc_val.alloc(static_cast<size_t>(K.nnz())));
+    SMG_CUDA(h, h->auk_val.alloc(static_cast<size_t>(K.nnz())));
+    // Auk by row (ascending known column inside a row), rows in permuted order
+    std::vector<int> rp(static_cast<size_t>(nu) + 1, 0), rq(K.nnz()), rpos(K.nnz());
+    {
+      std::vector<int> cnt(static_cast<size_t>(nu) + 1, 0);
+      for (int p = 0; p < K.nnz(); p++) cnt[K.rowidx[p] + 1]++;
+      for (int i = 0; i < nu; i++) cnt[i + 1] += cnt[i];
+      std::vector<int> q0(K.nnz()), pos0(K.nnz());
+      std::vector<int> nx(cnt.begin(), cnt.end() - 1);
+      for (int c = 0; c < nk; c++)
+        for (int p = K.colptr[c]; p < K.colptr[c + 1]; p++) {
+          const int d = nx[K.rowidx[p]]++;
+          q0[d] = c;
+          pos0[d] = p;
+        }
+      int o = 0;
+      for (int r = 0; r < nu; r++) {
+        const int row = perm0[r];
+        rp[r] = o;
+        for (int t = cnt[row]; t < cnt[row + 1]; t++, o++) {
+          rq[o] = q0[t];
+          rpos[o] = pos0[t];
+        }
+      }
+      rp[nu] = o;
+    }
+    SMG_CUDA(h, h->auk_ptr.upload(rp, st));
+    SMG_CUDA(h, h->auk_q.upload(rq, st));
+    SMG_CUDA(h, h->auk_pos.upload(rpos, st));
+    // z(known) = known_val via igl::slice_into (cpp:355): sequential writes, the last
+    // occurrence of a repeated index wins
+    std::vector<int> last(static_cast<size_t>(pl.n), -1);
+    for (int i = 0; i < nk; i++) last[pl.known[i]] = i;
+    std::vector<int> kidx, ksrc;
+    for (int i = 0; i < pl.n; i++)
+      if (last[i] >= 0) {
+        kidx.push_back(i);
+        ksrc.push_back(last[i]);
+      }
+    h->n_known_distinct = static_cast<int>(kidx.size());
+    SMG_CUDA(h, h->kidx.upload(kidx, st));
+    SMG_CUDA(h, h->ksrc.upload(ksrc, st));
+  }
+  SMG_TRY(check_launch(h, "upload plan"));
+  SMG_CUDA(h, cudaStreamSynchronize(st));  // host vectors above go out of scope
+  return SMG_OK;
+}
+
+int check_ready(const smg_handle* h, bool need_device) {
+  if (!h) return SMG_E_INVALID;
+  if (!h->have_plan) return fail(const_cast<smg_handle*>(h), SMG_E_STATE, "smg_precompute has not been called");
+  if (need_device && h->plan_only)
+    return fail(const_cast<smg_handle*>(h), SMG_E_STATE, "plan-only handle (SMG_DEVICE_NONE) cannot compute");
+  return SMG_OK;
+}
+
+int set_device(smg_handle* h) {
+  if (h->plan_only) return SMG_OK;
+  SMG_CUDA(h, cudaSetDevice(h->device));
+  return SMG_OK;
+}
+
+// host (reference numbering, n x k) -> level work vector (permuted numbering)
+int stage_in(smg_handle* h, int l, const double* host, DevBuf<double>& stage, double* dst, int k) {
+  LevelDev& L = h->lv[l];
+  const size_t cnt = static_cast<size_t>(L.n) * k;
+  SMG_CUDA(h, stage.reserve(cnt));
+  if (cnt == 0) return SMG_OK;
+  SMG_CUDA(h, cudaMemcpyAsync(stage.p, host, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  smg::launch_permute_in(stage.p, L.perm.p, dst, L.n, k, h->stream);
+  h->launches++;
+  return SMG_OK;
+}
+
+int stage_out(smg_handle* h, int l, const double* src, DevBuf<double>& stage, double* host, int k) {
+  LevelDev& L = h->lv[l];
+  const size_t cnt = static_cast<size_t>(L.n) * k;
+  SMG_CUDA(h, stage.reserve(cnt));
+  if (cnt == 0) return SMG_OK;
+  smg::launch_permute_out(src, L.perm.p, stage.p, L.n, k, h->stream);
+  h->launches++;
+  SMG_CUDA(h, cudaMemcpyAsync(host, stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return check_launch(h, "stage_out");
+}
+
+int valid_level(smg_handle* h, int lv, bool need_coarser) {
+  const int nlev = static_cast<int>(h->lv.size());
+  if (lv < 0 || lv >= nlev || (need_coarser && lv + 1 >= nlev))
+    return fail(h, SMG_E_INVALID, "level out of range");
+  return SMG_OK;
+}
+
+// min_quad_with_fixed_mg_solve on device pointers
+int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const double* d_z0, int k,
+               double tol, int max_iter, double* d_z, double* r_his, int* n_his, int* converged) {
+  smg::Plan& pl = h->plan;
+  LevelDev& L0 = h->lv[0];
+  const int nu = L0.n;
+  const int nk = pl.has_fixed ? static_cast<int>(pl.known.size()) : 0;
+  SMG_TRY(ensure_k(h, k));
+  // z_unknown = z0(unknown); RHS_unknown = RHS(unknown) - Auk * known_val  (cpp:310-318)
+  const bool with_auk = pl.has_fixed && nk > 0 && pl.Auk.nnz() > 0;
+  if (with_auk && !d_kv) return fail(h, SMG_E_INVALID, "known_val is required");
+  smg::launch_gather_system(d_RHS, d_z0, d_kv, pl.n, nk, h->g.p, with_auk ? h->auk_ptr.p : nullptr,
+                            h->auk_q.p, h->auk_val.p, L0.b.p, L0.u.p, nu, k, h->stream);
+  h->launches++;
+  double residual = 0.0;
+  int nh = 0;
+  for (int iter = 0; iter < max_iter; iter++) {  // cpp:330-347 / :108-125
+    SMG_TRY(residual_norm_device(h, 0, L0.b.p, L0.u.p, k, &residual));
+    r_his[nh++] = residual;
+    if (h->opt.verbose) std::printf("%.17g\n", residual);
+    if (!std::isfinite(residual)) {
+      *n_his = nh;
+      *converged = 0;
+      return fail(h, SMG_E_NONFINITE, "residual is not finite");
+    }
+    if (residual < tol) break;
+    SMG_TRY(vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k));
+  }
+  if (h->opt.verbose) std::printf("residual norm: %.17g\n", residual);
+  // z(unknown) = z_unknown ; z(known) = known_val   (cpp:353-355)
+  smg::launch_scatter_solution(L0.u.p, h->g.p, d_z, pl.n, nu, k, h->stream);
+  h->launches++;
+  if (pl.has_fixed && h->n_known_distinct > 0) {
+    if (!d_kv) return fail(h, SMG_E_INVALID, "known_val is required");
+    smg::launch_scatter_known(d_kv, h->kidx.p, h->ksrc.p, d_z, pl.n, nk, h->n_known_distinct, k,
+                              h->stream);
+    h->launches++;
+  }
+  SMG_TRY(check_launch(h, "solve"));
+  *n_his = nh;
+  *converged = residual > tol ? 0 : 1;  // cpp:357-360 (stale residual, by design)
+  return SMG_OK;
+}
+
+Csc make_csc(int rows, int cols, const int* colptr, const int* rowidx, const double* val) {
+  Csc m;
+  m.rows = rows;
+  m.cols = cols;
+  m.colptr.assign(colptr, colptr + cols + 1);
+  const int nnz = m.colptr[cols];
+  m.rowidx.assign(rowidx, rowidx + nnz);
+  if (val) m.val.assign(val, val + nnz);
+  return m;
+}
+
+bool csc_valid(int rows, int cols, const int* colptr, const int* rowidx, bool sorted_required) {
+  if (rows < 0 || cols < 0 || !colptr || colptr[0] != 0) return false;
+  for (int j = 0; j < cols; j++)
+    if (colptr[j + 1] < colptr[j]) return false;
+  if (colptr[cols] > 0 && !rowidx) return false;
+  for (int j = 0; j < cols; j++)
+    for (int p = colptr[j]; p < colptr[j + 1]; p++) {
+      if (rowidx[p] < 0 || rowidx[p] >= rows) return false;
+      if (sorted_required && p > colptr[j] && rowidx[p] <= rowidx[p - 1]) return false;
+    }
+  return true;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+void smg_default_options(smg_options* opt) {
+  if (!opt) return;
+  std::memset(opt, 0, sizeof(*opt));
+  opt->pre_relax = 2;
+  opt->post_relax = 2;
+  opt->smoother = SMG_SMOOTHER_MULTICOLOUR;
+  opt->device = SMG_DEVICE_CURRENT;
+  opt->use_graph = 1;
+  opt->verbose = 0;
+  opt->locality_reorder = 1;
+  opt->sigma = 256;
+}
+
+int smg_version(void) { return SMG_VERSION; }
+
+const char* smg_status_string(int status) {
+  switch (status) {
+    case SMG_OK: return "ok";
+    case SMG_E_INVALID: return "invalid argument";
+    case SMG_E_CUDA: return "CUDA error or no device";
+    case SMG_E_NLEVELS: return "at least 2 multigrid levels are required";
+    case SMG_E_NONFINITE: return "non-finite residual";
+    case SMG_E_STATE: return "call order violated";
+    case SMG_E_CUSOLVER: return "coarse factorisation failed";
+    case SMG_E_NCCL: return "NCCL error";
+    case SMG_E_NOT_SYMMETRIC: return "matrix pattern is not symmetric";
+    case SMG_E_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown status";
+}
+
+const char* smg_last_error(const smg_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int smg_create(smg_handle** out, const smg_options* opt) {
+  if (!out) return SMG_E_INVALID;
+  *out = nullptr;
+  smg_handle* h = new smg_handle();
+  if (opt) h->opt = *opt;
+  else smg_default_options(&h->opt);
+  if (h->opt.smoother != SMG_SMOOTHER_WAVEFRONT && h->opt.smoother != SMG_SMOOTHER_MULTICOLOUR) {
+    delete h;
+    return SMG_E_INVALID;
+  }
+  if (h->opt.device == SMG_DEVICE_NONE) {
+    h->plan_only = true;
+    *out = h;
+    return SMG_OK;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    delete h;
+    return SMG_E_CUDA;  // no CPU fallback, by design
+  }
+  int dev = h->opt.device;
+  if (dev == SMG_DEVICE_CURRENT) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      delete h;
+      return SMG_E_CUDA;
+    }
+  }
+  if (dev < 0 || dev >= ndev || cudaSetDevice(dev) != cudaSuccess) {
+    delete h;
+    return SMG_E_CUDA;
+  }
+  h->device = dev;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 64 * sizeof(double)) != cudaSuccess) {
+    smg_destroy(h);
+    return SMG_E_CUDA;
+  }
+  if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS ||
+      cusolverDnSetStream(h->cusolver, h->stream) != CUSOLVER_STATUS_SUCCESS) {
+    smg_destroy(h);
+    return SMG_E_CUSOLVER;
+  }
+  *out = h;
+  return SMG_OK;
+}
+
+void smg_destroy(smg_handle* h) {
+  if (!h) return;
+  if (!h->plan_only && h->device >= 0) {
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
+    if (h->cusolver) cusolverDnDestroy(h->cusolver);
+    if (h->h_norm) cudaFreeHost(h->h_norm);
+    h->lv.clear();
+    // remaining DevBufs are released by the destructor below, before the stream
+    h->a_in.release(); h->lhs_src.release(); h->auk_src.release(); h->g.release();
+    h->auk_ptr.release(); h->auk_q.release(); h->auk_pos.release();
+    h->auk_csc_val.release(); h->auk_val.release(); h->kidx.release(); h->ksrc.release();
+    h->ainv.release(); h->potrf_work.release(); h->dev_info.release();
+    h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
+    h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int smg_set_hierarchy(smg_handle* h, int n_levels, const int* n_rows, const int* const* P_colptr,
+                      const int* const* P_rowidx, const double* const* P_val) {
+  if (!h) return SMG_E_INVALID;
+  if (n_levels < 2) return fail(h, SMG_E_NLEVELS, "at least 2 multigrid levels are required");
+  if (!n_rows || !P_colptr || !P_rowidx || !P_val) return fail(h, SMG_E_INVALID, "null argument");
+  std::vector<Csc> P;
+  for (int l = 1; l < n_levels; l++) {
+    const int rows = n_rows[l - 1], cols = n_rows[l];
+    if (!P_colptr[l - 1] || !P_val[l - 1] ||
+        !csc_valid(rows, cols, P_colptr[l - 1], P_rowidx[l - 1], true))
+      return fail(h, SMG_E_INVALID,
+                  "prolongation " + std::to_string(l) + " is not a valid sorted CSC matrix");
+    P.push_back(make_csc(rows, cols, P_colptr[l - 1], P_rowidx[l - 1], P_val[l - 1]));
+  }
+  h->n_rows.assign(n_rows, n_rows + n_levels);
+  h->P_full = std::move(P);
+  h->have_hierarchy = true;
+  h->have_plan = false;
+  return SMG_OK;
+}
+
+int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowidx,
+                   const double* A_val, const int* known, int n_known) {
+  if (!h) return SMG_E_INVALID;
+  if (!h->have_hierarchy) return fail(h, SMG_E_STATE, "smg_set_hierarchy has not been called");
+  if (!A_colptr || !A_val || (n_known > 0 && !known)) return fail(h, SMG_E_INVALID, "null argument");
+  if (n != h->n_rows[0]) return fail(h, SMG_E_INVALID, "A does not match the finest level size");
+  if (!csc_valid(n, n, A_colptr, A_rowidx, true))
+    return fail(h, SMG_E_INVALID, "A is not a valid sorted CSC matrix");
+  SMG_TRY(set_device(h));
+  h->have_plan = false;
+  const double t0 = now_ms();
+  Csc A = make_csc(n, n, A_colptr, A_rowidx, nullptr);
+  smg::PlanOptions po;
+  po.smoother = h->opt.smoother;
+  po.locality_reorder = h->opt.locality_reorder;
+  po.sigma = h->opt.sigma > 0 ? h->opt.sigma : 1;
+  const int rc = smg::build_plan(A, known, n_known, h->P_full, po, &h->plan);
+  if (rc != SMG_OK) return fail(h, rc, h->plan.error);
+  const double t1 = now_ms();
+  h->timings[3] = t1 - t0;
+  if (h->plan_only) {
+    h->have_plan = true;
+    return SMG_OK;
+  }
+  SMG_TRY(upload_plan(h));
+  const int nnz = A_colptr[n];
+  SMG_CUDA(h, h->a_in.reserve(static_cast<size_t>(nnz)));
+  SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
+                              h->stream));
+  SMG_TRY(numeric_setup(h));
+  h->timings[4] = now_ms() - t1;
+  h->have_plan = true;
+  return SMG_OK;
+}
+
+int smg_update_values(smg_handle* h, const double* A_val) {
+  SMG_TRY(check_ready(h, true));
+  if (!A_val) return fail(h, SMG_E_INVALID, "null argument");
+  SMG_TRY(set_device(h));
+  const double t0 = now_ms();
+  const size_t nnz = h->a_in.n;
+  SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
+                              h->stream));
+  SMG_TRY(numeric_setup(h));
+  h->timings[3] = 0.0;
+  h->timings[4] = now_ms() - t0;
+  return SMG_OK;
+}
+
+int smg_solve_device(smg_handle* h, const double* d_RHS, const double* d_known_val,
+                     const double* d_z0, int k, double tol, int max_iter, double* d_z,
+                     double* r_his, int* n_his, int* converged) {
+  SMG_TRY(check_ready(h, true));
+  if (!d_RHS || !d_z0 || !d_z || !r_his || !n_his || !converged || k < 1 || max_iter < 0)
+    return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  const double t0 = now_ms();
+  const int rc = solve_core(h, d_RHS, d_known_val, d_z0, k, tol, max_iter, d_z, r_his, n_his,
+                            converged);
+  if (rc == SMG_OK) SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->timings[0] = h->timings[2] = 0.0;
+  h->timings[1] = now_ms() - t0;
+  return rc;
+}
+
+int smg_solve(smg_handle* h, const double* RHS, const double* known_val, const double* z0, int k,
+              double tol, int max_iter, double* z, double* r_his, int* n_his, int* converged) {
+  SMG_TRY(check_ready(h, true));
+  if (!RHS || !z0 || !z || !r_his || !n_his || !converged || k < 1 || max_iter < 0)
+    return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  const smg::Plan& pl = h->plan;
+  const size_t cnt = static_cast<size_t>(pl.n) * k;
+  const size_t nk = pl.has_fixed ? pl.known.size() : 0;
+  if (nk > 0 && !known_val) return fail(h, SMG_E_INVALID, "known_val is required");
+  const double t0 = now_ms();
+  SMG_CUDA(h, h->st_a.reserve(cnt));
+  SMG_CUDA(h, h->st_b.reserve(cnt));
+  SMG_CUDA(h, h->st_c.reserve(cnt));
+  SMG_CUDA(h, h->st_d.reserve(nk * k));
+  SMG_CUDA(h, cudaMemcpyAsync(h->st_a.p, RHS, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SMG_CUDA(h, cudaMemcpyAsync(h->st_b.p, z0, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (nk > 0)
+    SMG_CUDA(h, cudaMemcpyAsync(h->st_d.p, known_val, nk * k * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double t1 = now_ms();
+  const int rc = solve_core(h, h->st_a.p, nk > 0 ? h->st_d.p : nullptr, h->st_b.p, k, tol,
+                            max_iter, h->st_c.p, r_his, n_his, converged);
+  if (rc != SMG_OK) return rc;
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double t2 = now_ms();
+  SMG_CUDA(h, cudaMemcpyAsync(z, h->st_c.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double t3 = now_ms();
+  h->timings[0] = t1 - t0;
+  h->timings[1] = t2 - t1;
+  h->timings[2] = t3 - t2;
+  return SMG_OK;
+}
+
+// ---- mg_VCycle.h operators -------------------------------------------------------
+int smg_vcycle(smg_handle* h, int lv, int pre, int post, const double* B, double* u, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!B || !u || k < 1 || pre < 0 || post < 0) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  LevelDev& L = h->lv[lv];
+  SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
+  SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
+  SMG_TRY(vcycle_run(h, lv, pre, post, k));
+  return stage_out(h, lv, L.u.p, h->st_a, u, k);
+}
+
+int smg_relax(smg_handle* h, int lv, int iters, const double* B, double* u, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!B || !u || k < 1 || iters < 0) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  LevelDev& L = h->lv[lv];
+  SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
+  SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
+  relax_device(h, lv, iters, L.b.p, L.u.p, k);
+  return stage_out(h, lv, L.u.p, h->st_a, u, k);
+}
+
+int smg_apply_A(smg_handle* h, int lv, const double* u, double* Au, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!u || !Au || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  LevelDev& L = h->lv[lv];
+  SMG_TRY(stage_in(h, lv, u, h->st_a, L.u.p, k));
+  apply_A_device(h, lv, L.u.p, L.r.p, k);
+  return stage_out(h, lv, L.r.p, h->st_a, Au, k);
+}
+
+int smg_residual(smg_handle* h, int lv, const double* B, const double* u, double* r, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!B || !u || !r || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  LevelDev& L = h->lv[lv];
+  SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
+  SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
+  residual_device(h, lv, L.b.p, L.u.p, L.r.p, k);
+  return stage_out(h, lv, L.r.p, h->st_a, r, k);
+}
+
+int smg_residual_norm(smg_handle* h, int lv, const double* B, const double* u, int k,
+                      double* norm) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!B || !u || !norm || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  LevelDev& L = h->lv[lv];
+  SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
+  SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
+  return residual_norm_device(h, lv, L.b.p, L.u.p, k, norm);
+}
+
+int smg_restrict(smg_handle* h, int lv, const double* x, double* Rx, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, true));
+  if (!x || !Rx || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  SMG_TRY(stage_in(h, lv, x, h->st_a, h->lv[lv].r.p, k));
+  restrict_device(h, lv, h->lv[lv].r.p, h->lv[lv + 1].b.p, k);
+  return stage_out(h, lv + 1, h->lv[lv + 1].b.p, h->st_a, Rx, k);
+}
+
+int smg_prolong(smg_handle* h, int lv, const double* x, double* Px, int k) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, true));
+  if (!x || !Px || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  SMG_TRY(stage_in(h, lv + 1, x, h->st_a, h->lv[lv + 1].u.p, k));
+  prolong_device(h, lv, h->lv[lv + 1].u.p, h->lv[lv].r.p, k, false);
+  return stage_out(h, lv, h->lv[lv].r.p, h->st_a, Px, k);
+}
+
+int smg_coarse_solve(smg_handle* h, const double* B, double* u, int k) {
+  SMG_TRY(check_ready(h, true));
+  if (!B || !u || k < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  const int last = static_cast<int>(h->lv.size()) - 1;
+  LevelDev& L = h->lv[last];
+  SMG_TRY(stage_in(h, last, B, h->st_a, L.b.p, k));
+  SMG_TRY(stage_in(h, last, u, h->st_b, L.u.p, k));
+  coarse_solve_device(h, L.b.p, L.u.p, k);
+  return stage_out(h, last, L.u.p, h->st_a, u, k);
+}
+
+// ---- index / topology outputs ------------------------------------------------------
+int smg_num_levels(const smg_handle* h) {
+  if (!h) return -1;
+  if (h->have_plan) return static_cast<int>(h->plan.lv.size());
+  return h->have_hierarchy ? static_cast<int>(h->n_rows.size()) : -1;
+}
+
+int smg_level_rows(const smg_handle* h, int lv) {
+  if (!h || !h->have_plan || lv < 0 || lv >= static_cast<int>(h->plan.lv.size())) return -1;
+  return h->plan.lv[lv].n;
+}
+
+int smg_num_unknown(const smg_handle* h) {
+  if (!h || !h->have_plan) return -1;
+  return static_cast<int>(h->plan.unknown.size());
+}
+
+int smg_get_unknown(const smg_handle* h, int* unknown) {
+  SMG_TRY(check_ready(h, false));
+  if (!unknown) return SMG_E_INVALID;
+  std::copy(h->plan.unknown.begin(), h->plan.unknown.end(), unknown);
+  return SMG_OK;
+}
+
+int smg_get_keep(const smg_handle* h, int lv, int* keep, int* n_keep) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 1 || lv >= static_cast<int>(h->plan.lv.size()) || !n_keep) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  if (!L.pruned) {
+    *n_keep = -1;
+    return SMG_OK;
+  }
+  *n_keep = static_cast<int>(L.keep.size());
+  if (keep) std::copy(L.keep.begin(), L.keep.end(), keep);
+  return SMG_OK;
+}
+
+static const Csc* pick_matrix(const smg_handle* h, int lv, int which) {
+  const smg::Plan& pl = h->plan;
+  const int nlev = static_cast<int>(pl.lv.size());
+  switch (which) {
+    case SMG_MAT_A: return (lv >= 0 && lv < nlev) ? &pl.lv[lv].A : nullptr;
+    case SMG_MAT_P: return (lv >= 1 && lv < nlev) ? &pl.lv[lv].P : nullptr;
+    case SMG_MAT_PT: return (lv >= 1 && lv < nlev) ? &pl.lv[lv].PT : nullptr;
+    case SMG_MAT_LHS: return &pl.LHS;
+    case SMG_MAT_AUK: return pl.has_fixed ? &pl.Auk : nullptr;
+  }
+  return nullptr;
+}
+
+int smg_matrix_dims(const smg_handle* h, int lv, int which, int* rows, int* cols, int* nnz) {
+  SMG_TRY(check_ready(h, false));
+  const Csc* m = pick_matrix(h, lv, which);
+  if (!m || !rows || !cols || !nnz) return SMG_E_INVALID;
+  *rows = m->rows;
+  *cols = m->cols;
+  *nnz = m->nnz();
+  return SMG_OK;
+}
+
+int smg_matrix_copy(smg_handle* h, int lv, int which, int* colptr, int* rowidx, double* val) {
+  SMG_TRY(check_ready(h, false));
+  const Csc* m = pick_matrix(h, lv, which);
+  if (!m) return fail(h, SMG_E_INVALID, "no such matrix");
+  if (colptr) std::copy(m->colptr.begin(), m->colptr.end(), colptr);
+  if (rowidx) std::copy(m->rowidx.begin(), m->rowidx.end(), rowidx);
+  if (!val || m->nnz() == 0) return SMG_OK;
+  if (which == SMG_MAT_P || which == SMG_MAT_PT) {
+    std::copy(m->val.begin(), m->val.end(), val);
+    return SMG_OK;
+  }
+  if (h->plan_only) return fail(h, SMG_E_STATE, "plan-only handle holds no matrix values");
+  SMG_TRY(set_device(h));
+  const double* src = nullptr;
+  if (which == SMG_MAT_A) src = h->lv[lv].a_val.p;
+  else if (which == SMG_MAT_LHS) {
+    // LHS values = caller's A gathered (mg[0].A additionally carries the 1e-12 shift
+    // only when level 0 is the coarsest, which nlev >= 2 excludes)
+    src = h->lv[0].a_val.p;
+  } else src = h->auk_csc_val.p;
+  SMG_CUDA(h, cudaMemcpyAsync(val, src, sizeof(double) * m->nnz(), cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMG_OK;
+}
+
+int smg_get_diag(smg_handle* h, int lv, double* diag) {
+  SMG_TRY(check_ready(h, true));
+  SMG_TRY(valid_level(h, lv, false));
+  if (!diag) return SMG_E_INVALID;
+  SMG_TRY(set_device(h));
+  return stage_out(h, lv, h->lv[lv].diag.p, h->st_a, diag, 1);
+}
+
+int smg_get_phases(const smg_handle* h, int lv, int* n_phases, int* phase_of_row) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !n_phases) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  *n_phases = L.n_phases;
+  if (phase_of_row) std::copy(L.phase.begin(), L.phase.end(), phase_of_row);
+  return SMG_OK;
+}
+
+int smg_level_padded_nnz(const smg_handle* h, int lv, int64_t* padded) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !padded) return SMG_E_INVALID;
+  *padded = h->plan.lv[lv].sellA.padded();
+  return SMG_OK;
+}
+
+// ---- measurement -----------------------------------------------------------------
+int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush_l2,
+                    float* ms_per_rep, int* launches_per_rep) {
+  SMG_TRY(check_ready(h, true));
+  if (!ms_per_rep || k < 1 || reps < 1) return fail(h, SMG_E_INVALID, "bad argument");
+  const bool need_coarser = which == SMG_K_RESTRICT || which == SMG_K_PROLONG_ADD;
+  if (which == SMG_K_COARSE_SOLVE) lv = static_cast<int>(h->lv.size()) - 1;
+  if (which == SMG_K_VCYCLE) lv = 0;
+  SMG_TRY(valid_level(h, lv, need_coarser));
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  const size_t flush_cnt = size_t(1) << 25;  // 256 MB of doubles > 126 MB L2
+  if (flush_l2) SMG_CUDA(h, h->flush.reserve(flush_cnt));
+  std::vector<cudaEvent_t> ev(static_cast<size_t>(reps) * 2);
+  for (auto& e : ev) SMG_CUDA(h, cudaEventCreate(&e));
+  LevelDev& L = h->lv[lv];
+  int64_t per_rep = 0;
+  int rc = SMG_OK;
+  for (int rep = -1; rep < reps && rc == SMG_OK; rep++) {  // rep -1 = warm-up
+    if (flush_l2) smg::launch_fill(h->flush.p, 1.0, static_cast<int64_t>(flush_cnt), h->stream);
+    const int64_t before = h->launches;
+    if (rep >= 0) cudaEventRecord(ev[2 * rep], h->stream);
+    switch (which) {
+      case SMG_K_RESIDUAL: residual_device(h, lv, L.b.p, L.u.p, L.r.p, k); break;
+      case SMG_K_RELAX_SWEEP: relax_device(h, lv, 1, L.b.p, L.u.p, k); break;
+      case SMG_K_RESTRICT: restrict_device(h, lv, L.r.p, h->lv[lv + 1].b.p, k); break;
+      case SMG_K_PROLONG_ADD: prolong_device(h, lv, h->lv[lv + 1].u.p, L.u.p, k, true); break;
+      case SMG_K_RESIDUAL_NORM: {
+        // device part only (no host read-back inside the timed region)
+        const int nb = smg::residual_norm_blocks(L.n);
+        if (h->norm_scratch.reserve(static_cast<size_t>(nb)) != cudaSuccess ||
+            h->norm_out.reserve(4) != cudaSuccess) {
+          rc = fail(h, SMG_E_CUDA, "alloc");
+          break;
+        }
+        smg::launch_residual_norm2(L.sellA.view(), L.b.p, L.u.p, L.n, std::min(k, smg::kMaxK),
+                                   h->norm_scratch.p, h->norm_out.p, h->stream);
+        h->launches += 2;
+        break;
+      }
+      case SMG_K_COARSE_SOLVE: coarse_solve_device(h, L.b.p, L.u.p, k); break;
+      case SMG_K_VCYCLE: rc = vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k); break;
+      default: rc = fail(h, SMG_E_INVALID, "unknown kernel id"); break;
+    }
+    if (rep >= 0) cudaEventRecord(ev[2 * rep + 1], h->stream);
+    per_rep = h->launches - before;
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  double total = 0.0;
+  if (rc == SMG_OK && e == cudaSuccess)
+    for (int rep = 0; rep < reps; rep++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[2 * rep], ev[2 * rep + 1]);
+      total += ms;
+    }
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (rc != SMG_OK) return rc;
+  if (e != cudaSuccess) return fail(h, SMG_E_CUDA, cudaGetErrorString(e));
+  SMG_TRY(check_launch(h, "time_kernel"));
+  *ms_per_rep = static_cast<float>(total / reps);
+  if (launches_per_rep) *launches_per_rep = static_cast<int>(per_rep);
+  return SMG_OK;
+}
+
+int64_t smg_launch_count(const smg_handle* h) { return h ? h->launches : 0; }
+
+int smg_get_timings(const smg_handle* h, double* ms, int n) {
+  if (!h || !ms || n < 0) return SMG_E_INVALID;
+  for (int i = 0; i < n && i < 8; i++) ms[i] = h->timings[i];
+  return SMG_OK;
+}
+
+void* smg_get_stream(const smg_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+}  // extern "C"

@@ -234,7 +234,7 @@ def pad_prolongation_to_three(S: sp.csc_matrix, F_coarse: np.ndarray) -> sp.csc_
     order = np.argsort(ekey, kind="stable")
     ekey_s, eface_s = ekey[order], eface[order]
     rows, cols, vals = [], [], []
-    indptr, indices, data = S.indptr, S.indices, S.data
+    indptr, indices, data = S.indptr.astype(np.int64), S.indices.astype(np.int64), S.data
     cnt = np.diff(indptr)
     # rows with one entry (coarse vertex copies)
     r1 = np.nonzero(cnt == 1)[0]

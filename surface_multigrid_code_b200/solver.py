@@ -1,0 +1,322 @@
+"""Host-side wrapper of one libsmg handle (``include/smg.h``).
+
+``Solver`` owns an ``smg_handle``: the multigrid hierarchy resident in HBM plus the
+precomputed Galerkin operators, and exposes the operators of the reference's
+``mg_VCycle.h`` / ``min_quad_with_fixed_mg.h`` on numpy arrays (copied in and out
+by the library) or on device pointers.  The reference-named free functions live in
+``reference_api.py``.
+
+Dense blocks follow Eigen: a 1-D array is a ``VectorXd``; a 2-D ``(n, k)`` array is a
+``MatrixXd`` and is handed over column-major.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class SmgError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{L.STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ip(a):
+    return a.ctypes.data_as(L._ip)
+
+
+def _dp(a):
+    return a.ctypes.data_as(L._dp)
+
+
+def _colmajor(a):
+    """(n,) or (n,k) -> (flat col-major float64 buffer, k, ndim)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        return np.ascontiguousarray(a), 1, 1
+    if a.ndim != 2:
+        raise ValueError("dense blocks must be 1-D or 2-D")
+    return np.ascontiguousarray(a.T).reshape(-1), a.shape[1], 2
+
+
+def _from_colmajor(buf, n, k, ndim):
+    if ndim == 1:
+        return buf
+    return np.asfortranarray(buf.reshape(k, n).T)
+
+
+class Solver:
+    """One libsmg handle.  ``device=None`` -> current CUDA device; ``device='none'``
+    -> plan-only handle (host index planning; every compute call raises)."""
+
+    def __init__(self, smoother: str = "multicolour", device=None, use_graph: bool = True,
+                 pre_relax: int = 2, post_relax: int = 2, verbose: bool = False,
+                 locality_reorder: bool = True, sigma: int = 256):
+        self._lib = L.load()
+        opt = L.smg_options()
+        self._lib.smg_default_options(C.byref(opt))
+        opt.smoother = {"wavefront": L.SMOOTHER_WAVEFRONT, "multicolour": L.SMOOTHER_MULTICOLOUR,
+                        "multicolor": L.SMOOTHER_MULTICOLOUR}[smoother]
+        if device is None:
+            opt.device = L.SMG_DEVICE_CURRENT
+        elif device == "none":
+            opt.device = L.SMG_DEVICE_NONE
+        else:
+            opt.device = int(device)
+        opt.use_graph = int(bool(use_graph))
+        opt.pre_relax = int(pre_relax)
+        opt.post_relax = int(post_relax)
+        opt.verbose = int(bool(verbose))
+        opt.locality_reorder = int(bool(locality_reorder))
+        opt.sigma = int(sigma)
+        self.smoother = smoother
+        self.plan_only = device == "none"
+        self._h = L._vp()
+        rc = self._lib.smg_create(C.byref(self._h), C.byref(opt))
+        if rc != L.SMG_OK:
+            self._h = None
+            raise SmgError(rc, "smg_create failed (no CUDA device? there is no CPU fallback)")
+        self.n = None
+        self.nknown = 0
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.smg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != L.SMG_OK:
+            raise SmgError(rc, self._lib.smg_last_error(self._h).decode())
+
+    # -- hierarchy / precompute ----------------------------------------------------
+    def set_hierarchy(self, P: Sequence):
+        """``P[l-1]`` = ``mg[l].P_full`` (scipy sparse, n_{l-1} x n_l), l = 1..nlev-1."""
+        Ps = []
+        for p in P:
+            p = p.tocsc()
+            if not p.has_sorted_indices:
+                p = p.copy()
+                p.sort_indices()
+            Ps.append(p)
+        nlev = len(Ps) + 1
+        n_rows = _i32([Ps[0].shape[0]] + [p.shape[1] for p in Ps]) if Ps else _i32([0])
+        keep = [(_i32(p.indptr), _i32(p.indices), _f64(p.data)) for p in Ps]
+        cp = (L._ip * max(len(Ps), 1))(*[_ip(k[0]) for k in keep])
+        ri = (L._ip * max(len(Ps), 1))(*[_ip(k[1]) for k in keep])
+        vv = (L._dp * max(len(Ps), 1))(*[_dp(k[2]) for k in keep])
+        self._check(self._lib.smg_set_hierarchy(self._h, nlev, _ip(n_rows), cp, ri, vv))
+        self.nlev = nlev
+        return self
+
+    def precompute(self, A, known: Optional[np.ndarray] = None):
+        """min_quad_with_fixed_mg_precompute; ``known=None`` selects the variant
+        without fixed values (src/min_quad_with_fixed_mg.cpp:3-51)."""
+        A = A.tocsc()
+        if not A.has_sorted_indices:
+            A = A.copy()
+            A.sort_indices()
+        cp, ri, vv = _i32(A.indptr), _i32(A.indices), _f64(A.data)
+        if known is None:
+            rc = self._lib.smg_precompute(self._h, A.shape[0], _ip(cp), _ip(ri), _dp(vv), None, -1)
+            self.nknown = 0
+        else:
+            kn = _i32(known)
+            rc = self._lib.smg_precompute(self._h, A.shape[0], _ip(cp), _ip(ri), _dp(vv), _ip(kn), kn.size)
+            self.nknown = int(kn.size)
+        self._check(rc)
+        self.n = A.shape[0]
+        self.nnz = int(cp[-1])
+        return self
+
+    def update_values(self, A_data):
+        vv = _f64(A_data)
+        if vv.size != self.nnz:
+            raise ValueError("value array does not match the precomputed pattern")
+        self._check(self._lib.smg_update_values(self._h, _dp(vv)))
+        return self
+
+    # -- solve ---------------------------------------------------------------------------
+    def solve(self, RHS, z0, known_val=None, tol: float = 1e-3, max_iter: int = 20):
+        """min_quad_with_fixed_mg_solve on host arrays -> (z, r_his, converged)."""
+        b, k, nd = _colmajor(RHS)
+        x0, k2, _ = _colmajor(z0)
+        if b.size != self.n * k or x0.size != b.size or k2 != k:
+            raise ValueError("RHS / z0 shape mismatch")
+        kv = None
+        if self.nknown > 0:
+            if known_val is None:
+                raise ValueError("known_val is required")
+            kv, k3, _ = _colmajor(known_val)
+            if kv.size != self.nknown * k or k3 != k:
+                raise ValueError("known_val shape mismatch")
+        z = np.empty(self.n * k)
+        r_his = np.zeros(max(int(max_iter), 1))
+        nh, conv = C.c_int(0), C.c_int(0)
+        rc = self._lib.smg_solve(self._h, _dp(b), _dp(kv) if kv is not None else None, _dp(x0), k,
+                                 float(tol), int(max_iter), _dp(z), _dp(r_his), C.byref(nh), C.byref(conv))
+        self._check(rc)
+        return _from_colmajor(z, self.n, k, nd), r_his[: nh.value].copy(), bool(conv.value)
+
+    def solve_device(self, d_RHS: int, d_known_val: Optional[int], d_z0: int, d_z: int, k: int = 1,
+                     tol: float = 1e-3, max_iter: int = 20):
+        """Same on raw device pointers (ints, e.g. ``tensor.data_ptr()``), col-major."""
+        r_his = np.zeros(max(int(max_iter), 1))
+        nh, conv = C.c_int(0), C.c_int(0)
+        rc = self._lib.smg_solve_device(self._h, d_RHS, d_known_val, d_z0, k, float(tol), int(max_iter),
+                                        d_z, _dp(r_his), C.byref(nh), C.byref(conv))
+        self._check(rc)
+        return r_his[: nh.value].copy(), bool(conv.value)
+
+    # -- mg_VCycle.h operators -------------------------------------------------------------
+    def level_rows(self, lv: int) -> int:
+        return int(self._lib.smg_level_rows(self._h, lv))
+
+    def num_levels(self) -> int:
+        return int(self._lib.smg_num_levels(self._h))
+
+    def vcycle(self, lv, B, u, pre=2, post=2):
+        b, k, nd = _colmajor(B)
+        x, _, _ = _colmajor(u)
+        x = x.copy()
+        self._check(self._lib.smg_vcycle(self._h, lv, pre, post, _dp(b), _dp(x), k))
+        return _from_colmajor(x, self.level_rows(lv), k, nd)
+
+    def relax(self, lv, iters, B, u):
+        b, k, nd = _colmajor(B)
+        x, _, _ = _colmajor(u)
+        x = x.copy()
+        self._check(self._lib.smg_relax(self._h, lv, iters, _dp(b), _dp(x), k))
+        return _from_colmajor(x, self.level_rows(lv), k, nd)
+
+    def apply_A(self, lv, u):
+        x, k, nd = _colmajor(u)
+        y = np.empty(self.level_rows(lv) * k)
+        self._check(self._lib.smg_apply_A(self._h, lv, _dp(x), _dp(y), k))
+        return _from_colmajor(y, self.level_rows(lv), k, nd)
+
+    def residual(self, lv, B, u):
+        b, k, nd = _colmajor(B)
+        x, _, _ = _colmajor(u)
+        r = np.empty(self.level_rows(lv) * k)
+        self._check(self._lib.smg_residual(self._h, lv, _dp(b), _dp(x), _dp(r), k))
+        return _from_colmajor(r, self.level_rows(lv), k, nd)
+
+    def residual_norm(self, lv, B, u) -> float:
+        b, k, _ = _colmajor(B)
+        x, _, _ = _colmajor(u)
+        out = C.c_double(0.0)
+        self._check(self._lib.smg_residual_norm(self._h, lv, _dp(b), _dp(x), k, C.byref(out)))
+        return float(out.value)
+
+    def restrict(self, lv, x):
+        xb, k, nd = _colmajor(x)
+        y = np.empty(self.level_rows(lv + 1) * k)
+        self._check(self._lib.smg_restrict(self._h, lv, _dp(xb), _dp(y), k))
+        return _from_colmajor(y, self.level_rows(lv + 1), k, nd)
+
+    def prolong(self, lv, x):
+        xb, k, nd = _colmajor(x)
+        y = np.empty(self.level_rows(lv) * k)
+        self._check(self._lib.smg_prolong(self._h, lv, _dp(xb), _dp(y), k))
+        return _from_colmajor(y, self.level_rows(lv), k, nd)
+
+    def coarse_solve(self, B, u):
+        b, k, nd = _colmajor(B)
+        x, _, _ = _colmajor(u)
+        x = x.copy()
+        self._check(self._lib.smg_coarse_solve(self._h, _dp(b), _dp(x), k))
+        return _from_colmajor(x, self.level_rows(self.num_levels() - 1), k, nd)
+
+    # -- index / topology outputs --------------------------------------------------------------
+    @property
+    def unknown(self) -> np.ndarray:
+        nu = self._lib.smg_num_unknown(self._h)
+        out = np.empty(max(nu, 0), dtype=np.int32)
+        self._check(self._lib.smg_get_unknown(self._h, _ip(out)))
+        return out
+
+    def keep(self, lv) -> Optional[np.ndarray]:
+        n = C.c_int(0)
+        self._check(self._lib.smg_get_keep(self._h, lv, None, C.byref(n)))
+        if n.value < 0:
+            return None
+        out = np.empty(n.value, dtype=np.int32)
+        self._check(self._lib.smg_get_keep(self._h, lv, _ip(out), C.byref(n)))
+        return out
+
+    def matrix(self, lv, which="A", values: bool = True):
+        import scipy.sparse as sp
+
+        w = L.MAT[which]
+        r, c, z = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.smg_matrix_dims(self._h, lv, w, C.byref(r), C.byref(c), C.byref(z)))
+        ip = np.empty(c.value + 1, dtype=np.int32)
+        ix = np.empty(max(z.value, 1), dtype=np.int32)
+        vv = np.zeros(max(z.value, 1), dtype=np.float64)
+        self._check(self._lib.smg_matrix_copy(self._h, lv, w, _ip(ip), _ip(ix), _dp(vv) if values else None))
+        m = sp.csc_matrix((r.value, c.value), dtype=np.float64)
+        m.indptr, m.indices, m.data = ip, ix[: z.value], vv[: z.value]
+        return m
+
+    def diag(self, lv) -> np.ndarray:
+        out = np.empty(self.level_rows(lv))
+        self._check(self._lib.smg_get_diag(self._h, lv, _dp(out)))
+        return out
+
+    def phases(self, lv):
+        n = C.c_int(0)
+        out = np.empty(self.level_rows(lv), dtype=np.int32)
+        self._check(self._lib.smg_get_phases(self._h, lv, C.byref(n), _ip(out)))
+        return n.value, out
+
+    def padded_nnz(self, lv) -> int:
+        v = C.c_int64(0)
+        self._check(self._lib.smg_level_padded_nnz(self._h, lv, C.byref(v)))
+        return int(v.value)
+
+    # -- measurement --------------------------------------------------------------------------
+    def time_kernel(self, which: str, lv: int = 0, k: int = 1, reps: int = 20, flush_l2: bool = False):
+        """-> (mean ms per rep, kernel launches per rep); CUDA events on the handle's stream."""
+        ms, nl = C.c_float(0.0), C.c_int(0)
+        self._check(self._lib.smg_time_kernel(self._h, L.KERNEL[which], lv, k, reps, int(flush_l2),
+                                              C.byref(ms), C.byref(nl)))
+        return float(ms.value), int(nl.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.smg_launch_count(self._h))
+
+    def timings(self):
+        out = np.zeros(8)
+        self._lib.smg_get_timings(self._h, _dp(out), 8)
+        return {"h2d_ms": out[0], "solve_ms": out[1], "d2h_ms": out[2], "plan_ms": out[3],
+                "precompute_device_ms": out[4]}
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.smg_get_stream(self._h) or 0)

@@ -1,0 +1,54 @@
+"""pytest configuration: the ``gpu`` marker and shared problem fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _ensure_built():
+    """Build the oracle and (if missing) libsmg.so once per session."""
+    from oracle import cpu_oracle
+
+    cpu_oracle.build()
+    from surface_multigrid_code_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    _ensure_built()
+
+
+@pytest.fixture(scope="session")
+def problems():
+    """Small seeded problems covering the reference's callers (03, 04, 05)."""
+    from surface_multigrid_code_b200 import meshgen as mg
+
+    out = {}
+    # 04-style: closed surface, a few pinned vertices, explicit-zero padded P (3 per row)
+    out["sphere_pad"] = mg.sphere_problem(4, 3, pad_three=True)
+    out["sphere"] = mg.sphere_problem(5, 4, pad_three=False, random_z0=True)
+    # 03-style: open surface, longest boundary loop pinned (drops coarse columns)
+    V, F = mg.grid_mesh(9, 7, jitter=0.2, seed=1)
+    out["grid"] = mg.mesh_subdivided_problem("grid", V, F, 3, 3, pad_three=True)
+    # 05-style: free variant, k = 3
+    V0, F0 = mg.octahedron()
+    Vs, Fs, P = mg.subdivision_hierarchy(V0, F0, 4, 3, project_sphere=True, pad_three=True)
+    Vs = mg.normalize_unit_area(Vs, Fs)
+    rng = np.random.default_rng(3)
+    U = Vs * (1.0 + 0.05 * rng.standard_normal((Vs.shape[0], 1)))
+    out["mcf"] = mg.mcf_step_problem(Vs, Fs, P, U=U)
+    return out
