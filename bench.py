@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- V-cycles/s of the surface-multigrid hot path on B200.
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "config 3"): octahedron
+subdivided 9x and projected to the sphere (1 048 578 vertices, nnz(A) = 7 340 034),
+A = -cotmatrix, b = voronoi mass, 6 pinned vertices, 5-level V(2,2) hierarchy with the
+reference's 3-entries-per-row prolongation layout, FP64.
+
+A "step" is one iteration of the loop of min_quad_with_fixed_mg_solve
+(src/min_quad_with_fixed_mg.cpp:330-347): one residual-norm measurement (with its host
+read-back) plus one V(2,2)-cycle.
+  value : steps/s with everything resident in HBM; every step is timed with CUDA events
+          on the library's stream and L2 is flushed (256 MB write) between steps.
+  e2e   : V-cycles/s through the public host-buffer call (smg_solve): per solve the RHS
+          and z0 are copied from pinned host memory, z and r_his come back; tol 1e-10.
+  roofline : the fine-level Gauss-Seidel sweep (dominant kernel), algorithmic bytes /
+          CUDA-event time, against MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle (single-thread C restatement of the reference path; the
+          reference itself needs Eigen and cannot be built here) on the same problem.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "V-cycles/sec (1M-vertex sphere Poisson, 5-level V(2,2), FP64)"
+UNIT = "V-cycles/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def build_problem(n_sub: int, n_levels: int):
+    from surface_multigrid_code_b200 import meshgen as mg
+
+    return mg.sphere_problem(n_sub, n_levels, tol=1e-10, max_iter=20, pad_three=True)
+
+
+def workload_config(pr, args, extra=None):
+    cfg = {
+        "workload": f"sphere_subdiv{args.subdiv}_{pr.n}v_{pr.nlev}level_poisson_fp64",
+        "vertices": int(pr.n),
+        "nnz_A": int(pr.A.nnz),
+        "levels": int(pr.nlev),
+        "rhs_columns": int(pr.k),
+        "pre_post": [2, 2],
+        "tol": pr.tol,
+        "data_layout": "reference P layout (3 stored entries per row, explicit zeros)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------
+# algorithmic bytes (int32 indices, fp64 values, k RHS columns)
+# --------------------------------------------------------------------------------------
+def bytes_gs_sweep(n, nnz, k=1):
+    return 12 * nnz + 4 * (n + 1) + 8 * n + 8 * n * k + 16 * n * k
+
+
+def bytes_residual(n, nnz, k=1):
+    return 12 * nnz + 4 * (n + 1) + 8 * n * k + 8 * n * k + 8 * n * k
+
+
+def bytes_residual_norm(n, nnz, k=1):
+    return 12 * nnz + 4 * (n + 1) + 8 * n * k + 8 * n * k
+
+
+def bytes_restrict(nf, nc, pnnz, k=1):
+    return 12 * pnnz + 4 * (nc + 1) + 8 * nf * k + 8 * nc * k
+
+
+def bytes_prolong_add(nf, nc, pnnz, k=1):
+    return 12 * pnnz + 8 * nc * k + 16 * nf * k
+
+
+def iteration_bytes(stats, k=1):
+    """Algorithmic bytes of one solve-loop iteration (residual norm + V(2,2))."""
+    tot = bytes_residual_norm(stats[0]["rows"], stats[0]["nnz"], k)
+    for l in range(len(stats) - 1):
+        n, nnz = stats[l]["rows"], stats[l]["nnz"]
+        nc, pnnz = stats[l + 1]["rows"], stats[l + 1]["p_nnz"]
+        tot += 4 * bytes_gs_sweep(n, nnz, k) + bytes_residual(n, nnz, k)
+        tot += bytes_restrict(n, nc, pnnz, k) + bytes_prolong_add(n, nc, pnnz, k)
+    nc = stats[-1]["rows"]
+    tot += 8 * nc * nc + 24 * nc * k  # dense inverse apply
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm (oracle): cpu_baseline of the GPU line and the whole --impl reference run
+# --------------------------------------------------------------------------------------
+def cpu_iterations(pr, warmup: int, steps: int):
+    """-> (seconds per step list, oracle).  One step = residual norm + V(2,2) on the
+    unknown-sized system, single thread (the reference path has no threading)."""
+    from oracle.cpu_oracle import Oracle
+
+    ora = Oracle(pr.P).precompute(pr.A, pr.known)
+    unknown = ora.unknown
+    bu = np.ascontiguousarray(pr.rhs[unknown])
+    zu = np.zeros_like(bu)
+    for _ in range(warmup):
+        zu, _ = ora.iterate(bu, zu, 1)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        zu, _ = ora.iterate(bu, zu, 1)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pr = build_problem(args.subdiv, args.levels)
+    times = cpu_iterations(pr, args.warmup, args.steps)
+    total = sum(times)
+    v = args.steps / total
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(pr, args, {"parallelism": "host cpu, 1 thread"}),
+        "cpu_baseline": {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{args.steps} solve-loop iterations (residual norm + V(2,2)) of the same problem; "
+                      "oracle/smg_oracle.c, single thread like the reference path (no threading in "
+                      "mg_VCycle.cpp); the reference itself needs Eigen 3.3.7 and cannot be built here",
+        },
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores_available": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+
+    from surface_multigrid_code_b200.solver import Solver
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pr = build_problem(args.subdiv, args.levels)
+    s = Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph)
+    t0 = time.perf_counter()
+    s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    t_pre = time.perf_counter() - t0
+    stats = [s.level_stats(l) for l in range(pr.nlev)]
+    n, k = pr.n, pr.k
+
+    # pinned host buffers for the end-to-end call
+    h_rhs = torch.from_numpy(np.ascontiguousarray(pr.rhs)).pin_memory()
+    h_z0 = torch.from_numpy(np.ascontiguousarray(pr.z0)).pin_memory()
+    h_kv = torch.from_numpy(np.ascontiguousarray(pr.known_val)).pin_memory()
+    h_z = torch.empty(n * k, dtype=torch.float64).pin_memory()
+    flush = torch.empty(1 << 25, dtype=torch.float64, device="cuda")  # 256 MB > L2
+
+    def solve_e2e():
+        return s.solve_host_ptr(h_rhs.data_ptr(), h_kv.data_ptr(), h_z0.data_ptr(), h_z.data_ptr(),
+                                k, pr.tol, pr.max_iter)
+
+    # correctness gate + warm-up of the whole path (graph capture, allocations)
+    r_his, ok = solve_e2e()
+    if not ok:
+        raise SystemExit(f"bench.py: solve did not converge: {r_his}")
+    cycles_per_solve = len(r_his) - 1
+    z = h_z.numpy()
+    A = pr.A.tocsr()
+    true_res = float(np.linalg.norm((pr.rhs - A @ z)[s.unknown]))
+    if not true_res < 10 * pr.tol:
+        raise SystemExit(f"bench.py: returned z does not satisfy the system: {true_res}")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident solve-loop iterations ---------------------------------------
+    s.time_kernel("mg_iteration", 0, k, max(args.warmup, 3), True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    l0 = s.launch_count
+    ms_iter, _ = s.time_kernel("mg_iteration", 0, k, args.steps, True)
+    launches = s.launch_count - l0
+    barrier()
+    total_ms = ms_iter * args.steps
+
+    # ---- e2e: host-buffer solves ---------------------------------------------------------
+    ext = torch.cuda.ExternalStream(s.stream)
+    e2e_ms, e2e_cycles = 0.0, 0
+    n_solves = max(3, min(10, args.steps))
+    with torch.cuda.stream(ext):
+        for i in range(-2, n_solves):
+            flush.fill_(1.0)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            r_his, ok = solve_e2e()
+            ev1.record()
+            ev1.synchronize()
+            if i >= 0:
+                e2e_ms += ev0.elapsed_time(ev1)
+                e2e_cycles += len(r_his) - 1
+    barrier()
+
+    # ---- per-kernel roofline numbers (rank-local, level 0) ----------------------------------
+    peak, peak_src = measured_peak()
+    reps = 20
+    kern = {}
+    n0, nnz0 = stats[0]["rows"], stats[0]["nnz"]
+    n1, p1 = stats[1]["rows"], stats[1]["p_nnz"]
+    for name, nbytes in (("relax_sweep", bytes_gs_sweep(n0, nnz0, k)),
+                         ("residual", bytes_residual(n0, nnz0, k)),
+                         ("residual_norm", bytes_residual_norm(n0, nnz0, k)),
+                         ("restrict", bytes_restrict(n0, n1, p1, k)),
+                         ("prolong_add", bytes_prolong_add(n0, n1, p1, k))):
+        ms, nl = s.time_kernel(name, 0, k, reps, True)
+        kern[name] = {"ms": ms, "launches": nl, "algorithmic_bytes": nbytes,
+                      "gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+    ms_v, nl_v = s.time_kernel("vcycle", 0, k, reps, True)
+    clk = clocks.stop()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("relax_sweep_dram_bytes")
+    except Exception:
+        pass
+    gs = kern["relax_sweep"]
+    roofline = {
+        "bound": "hbm", "kernel": "sell_gs_phase_kernel (fine-level Gauss-Seidel sweep, "
+                                  f"{gs['launches']} colour launches)",
+        "achieved": gs["gbs"], "peak": peak, "unit": "GB/s", "frac": gs["frac"], "traffic": traffic,
+        "peak_source": peak_src, "algorithmic_bytes_per_sweep": gs["algorithmic_bytes"],
+        "ms_per_sweep": gs["ms"],
+        "iteration": {"algorithmic_bytes": iteration_bytes(stats, k), "ms": ms_iter,
+                      "gbs": iteration_bytes(stats, k) / (ms_iter * 1e-3) / 1e9,
+                      "frac": iteration_bytes(stats, k) / (ms_iter * 1e-3) / 1e9 / peak},
+        "kernels": kern, "vcycle_ms": ms_v, "vcycle_launches": nl_v,
+    }
+
+    # ---- max over ranks -----------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(e2e_cycles)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    value = world * args.steps / (total_ms_max * 1e-3)
+    e2e_value = float(c[0]) / (e2e_ms_max * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nc = args.cpu_steps
+        times = cpu_iterations(pr, 1, nc)
+        cpu = {"value": nc / sum(times), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{nc} solve-loop iterations (residual norm + V(2,2)) of the same 1M problem, "
+                         "oracle/smg_oracle.c single thread (the reference path is single-threaded)",
+               "host_cores_available": os.cpu_count()}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(pr, args, {
+                "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one problem per GPU)",
+                "smoother": args.smoother, "cuda_graph": not args.no_graph,
+                "l2": "flushed between timed steps (256 MB write)",
+                "phases_per_level": [st["phases"] for st in stats],
+                "rows_per_level": [st["rows"] for st in stats],
+                "precompute_s": t_pre}),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(8 * (2 * n * k + h_kv.numel())),
+                    "d2h_bytes_per_step": int(8 * n * k + 8 * (cycles_per_solve + 1)),
+                    "step": f"one smg_solve call = {cycles_per_solve} V-cycles to tol {pr.tol}",
+                    "ms_per_solve": e2e_ms_max / n_solves, "solves": n_solves},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "final_residual": float(r_his[-1]), "true_residual": true_res,
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--subdiv", type=int, default=9, help="octahedron subdivisions (9 = 1M vertices)")
+    ap.add_argument("--levels", type=int, default=5)
+    ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "wavefront"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

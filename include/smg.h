@@ -170,6 +170,14 @@ int smg_get_phases(const smg_handle *h, int lv, int *n_phases, int *phase_of_row
 /* storage statistics of level lv's SELL-32 matrix: stored (padded) entries */
 int smg_level_padded_nnz(const smg_handle *h, int lv, int64_t *padded);
 
+/* level statistics for roofline arithmetic, out[8]:
+ *  [0] rows n_l  [1] stored entries of mg[lv].A (reference pattern, zeros included)
+ *  [2] entries of the compute pattern (what the kernels must read, unpadded)
+ *  [3] SELL-32 padded entries of A  [4] non-zero entries of mg[lv].P (lv >= 1)
+ *  [5] padded entries of P by fine row  [6] padded entries of PT by coarse row
+ *  [7] smoother phases */
+int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
+
 /* ---- measurement ----------------------------------------------------------
  * Times `reps` back-to-back launches of one hot-path kernel on level lv with k
  * right-hand sides using CUDA events on the handle's stream; returns the mean
@@ -183,7 +191,10 @@ typedef enum smg_kernel_id {
   SMG_K_PROLONG_ADD = 3,/* u_lv += P u_{lv+1} */
   SMG_K_RESIDUAL_NORM = 4,
   SMG_K_COARSE_SOLVE = 5,
-  SMG_K_VCYCLE = 6      /* one full V-cycle from level 0 (graph when enabled) */
+  SMG_K_VCYCLE = 6,     /* one full V-cycle from level 0 (graph when enabled) */
+  /* one iteration of the solve loop (min_quad_with_fixed_mg.cpp:330-347): residual
+   * norm with its host read-back, then one V-cycle */
+  SMG_K_MG_ITERATION = 7
 } smg_kernel_id;
 int smg_time_kernel(smg_handle *h, int which, int lv, int k, int reps, int flush_l2,
                     float *ms_per_rep, int *launches_per_rep);

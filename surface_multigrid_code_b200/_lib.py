@@ -43,6 +43,7 @@ KERNEL = {
     "residual_norm": 4,
     "coarse_solve": 5,
     "vcycle": 6,
+    "mg_iteration": 7,
 }
 
 
@@ -95,6 +96,7 @@ SIGNATURES = {
     "smg_get_diag": (C.c_int, [_vp, C.c_int, _dp]),
     "smg_get_phases": (C.c_int, [_vp, C.c_int, _ip, _ip]),
     "smg_level_padded_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "smg_level_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _ip]),
     "smg_launch_count": (C.c_int64, [_vp]),
     "smg_get_timings": (C.c_int, [_vp, _dp, C.c_int]),

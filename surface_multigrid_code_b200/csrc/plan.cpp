@@ -444,10 +444,13 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
     pl.known.assign(known, known + nknown);
     pl.unknown = setdiff_range(A.rows, known, nknown);                              // :156-158
     const int nu = static_cast<int>(pl.unknown.size());
-    pl.LHS = slice(Apat, pl.unknown.data(), nu, pl.unknown.data(), nu, &pl.lhs_src);  // :167
-    pl.Auk = slice(Apat, pl.unknown.data(), nu, pl.known.data(), nknown, &pl.auk_src);  // :170
+    static const int kEmpty = 0;  // slice(): a null index list means "all", so never pass one
+    const int* kn = nknown > 0 ? pl.known.data() : &kEmpty;
+    const int* un = nu > 0 ? pl.unknown.data() : &kEmpty;
+    pl.LHS = slice(Apat, un, nu, un, nu, &pl.lhs_src);      // :167
+    pl.Auk = slice(Apat, un, nu, kn, nknown, &pl.auk_src);  // :170
     for (int l = 1; l < nlev; l++) pl.lv[l].P = P_full[l - 1];
-    pl.lv[1].P = slice(P_full[0], pl.unknown.data(), nu, nullptr, 0, nullptr);  // :185
+    pl.lv[1].P = slice(P_full[0], un, nu, nullptr, 0, nullptr);  // :185
     for (int l = 1; l < nlev; l++) {                                            // :186-220
       Csc& P = pl.lv[l].P;
       std::vector<int> keep;

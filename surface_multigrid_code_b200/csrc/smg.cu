@@ -1122,6 +1122,23 @@ int smg_level_padded_nnz(const smg_handle* h, int lv, int64_t* padded) {
   return SMG_OK;
 }
 
+int smg_level_stats(const smg_handle* h, int lv, int64_t* out) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !out) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  int64_t pnz = 0;
+  for (double v : L.P.val) pnz += (v != 0.0);
+  out[0] = L.n;
+  out[1] = L.A.nnz();
+  out[2] = L.Alive.nnz();
+  out[3] = L.sellA.padded();
+  out[4] = pnz;
+  out[5] = L.sellP.padded();
+  out[6] = L.sellPT.padded();
+  out[7] = L.n_phases;
+  return SMG_OK;
+}
+
 // ---- measurement -----------------------------------------------------------------
 int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush_l2,
                     float* ms_per_rep, int* launches_per_rep) {
@@ -1129,7 +1146,7 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
   if (!ms_per_rep || k < 1 || reps < 1) return fail(h, SMG_E_INVALID, "bad argument");
   const bool need_coarser = which == SMG_K_RESTRICT || which == SMG_K_PROLONG_ADD;
   if (which == SMG_K_COARSE_SOLVE) lv = static_cast<int>(h->lv.size()) - 1;
-  if (which == SMG_K_VCYCLE) lv = 0;
+  if (which == SMG_K_VCYCLE || which == SMG_K_MG_ITERATION) lv = 0;
   SMG_TRY(valid_level(h, lv, need_coarser));
   SMG_TRY(set_device(h));
   SMG_TRY(ensure_k(h, k));
@@ -1164,6 +1181,12 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
       }
       case SMG_K_COARSE_SOLVE: coarse_solve_device(h, L.b.p, L.u.p, k); break;
       case SMG_K_VCYCLE: rc = vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k); break;
+      case SMG_K_MG_ITERATION: {
+        double res = 0.0;
+        rc = residual_norm_device(h, 0, L.b.p, L.u.p, k, &res);
+        if (rc == SMG_OK) rc = vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k);
+        break;
+      }
       default: rc = fail(h, SMG_E_INVALID, "unknown kernel id"); break;
     }
     if (rep >= 0) cudaEventRecord(ev[2 * rep + 1], h->stream);

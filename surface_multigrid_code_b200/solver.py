@@ -182,6 +182,19 @@ class Solver:
         self._check(rc)
         return _from_colmajor(z, self.n, k, nd), r_his[: nh.value].copy(), bool(conv.value)
 
+    def solve_host_ptr(self, RHS_ptr: int, known_val_ptr: Optional[int], z0_ptr: int, z_ptr: int,
+                       k: int = 1, tol: float = 1e-3, max_iter: int = 20):
+        """smg_solve on raw HOST addresses (e.g. pinned buffers): no conversion copies.
+        Buffers are n x k col-major float64 (known_val: nknown x k)."""
+        r_his = np.zeros(max(int(max_iter), 1))
+        nh, conv = C.c_int(0), C.c_int(0)
+        cast = lambda p: C.cast(C.c_void_p(p), L._dp) if p else None
+        rc = self._lib.smg_solve(self._h, cast(RHS_ptr), cast(known_val_ptr), cast(z0_ptr), k,
+                                 float(tol), int(max_iter), cast(z_ptr), _dp(r_his), C.byref(nh),
+                                 C.byref(conv))
+        self._check(rc)
+        return r_his[: nh.value].copy(), bool(conv.value)
+
     def solve_device(self, d_RHS: int, d_known_val: Optional[int], d_z0: int, d_z: int, k: int = 1,
                      tol: float = 1e-3, max_iter: int = 20):
         """Same on raw device pointers (ints, e.g. ``tensor.data_ptr()``), col-major."""
@@ -298,6 +311,12 @@ class Solver:
         v = C.c_int64(0)
         self._check(self._lib.smg_level_padded_nnz(self._h, lv, C.byref(v)))
         return int(v.value)
+
+    def level_stats(self, lv) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.smg_level_stats(self._h, lv, out))
+        keys = ("rows", "nnz_ref", "nnz", "padded", "p_nnz", "p_padded", "pt_padded", "phases")
+        return dict(zip(keys, [int(v) for v in out]))
 
     # -- measurement --------------------------------------------------------------------------
     def time_kernel(self, which: str, lv: int = 0, k: int = 1, reps: int = 20, flush_l2: bool = False):

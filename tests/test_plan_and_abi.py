@@ -1,0 +1,129 @@
+"""CPU tests of the host side of libsmg.so: the C ABI loads and exports every symbol
+include/smg.h declares; the index/topology planning (plan-only handles, no CUDA) is
+bit-identical to the oracle; there is no CPU fallback."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util
+from oracle.cpu_oracle import Oracle
+from surface_multigrid_code_b200 import _lib
+from surface_multigrid_code_b200.solver import SmgError, Solver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "smg.h")).read()
+    declared = set(re.findall(r"^(?:int|void|const char|int64_t)\s*\**\s*(smg_\w+)\s*\(", header, re.M))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in smg.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.smg_version() == 100
+    assert lib.smg_status_string(2) == b"CUDA error or no device"
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(SmgError) as e:
+        Solver()
+    assert e.value.status == 2  # SMG_E_CUDA
+
+
+def test_plan_only_handle_refuses_compute(problems):
+    pr = problems["sphere_pad"]
+    s = Solver(device="none").set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    for call in (lambda: s.solve(pr.rhs, pr.z0, pr.known_val),
+                 lambda: s.relax(0, 1, np.zeros(s.level_rows(0)), np.zeros(s.level_rows(0))),
+                 lambda: s.time_kernel("residual")):
+        with pytest.raises(SmgError) as e:
+            call()
+        assert e.value.status == 5  # SMG_E_STATE
+
+
+def _check_index_outputs(P, A, known, smoother):
+    ora = Oracle(P).precompute(A, known)
+    s = Solver(smoother=smoother, device="none").set_hierarchy(P).precompute(A, known)
+    nlev = len(P) + 1
+    assert s.num_levels() == nlev
+    assert np.array_equal(s.unknown, ora.unknown)
+    for lv in range(nlev):
+        assert s.level_rows(lv) == ora.level_rows(lv)
+        a, b = s.matrix(lv, "A", values=False), ora.matrix(lv, "A")
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        if lv >= 1:
+            ks, ko = s.keep(lv), ora.keep(lv)
+            assert (ks is None) == (ko is None)
+            if ks is not None:
+                assert np.array_equal(ks, ko)
+            for w in ("P", "PT"):
+                a, b = s.matrix(lv, w), ora.matrix(lv, w)
+                assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+                assert np.array_equal(a.data, b.data)
+    if known is not None:
+        for w in ("LHS", "Auk"):
+            a, b = s.matrix(0, w, values=False), ora.matrix(0, w)
+            assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    return s, ora
+
+
+@pytest.mark.parametrize("name", ["sphere_pad", "sphere", "grid", "mcf"])
+@pytest.mark.parametrize("smoother", ["multicolour", "wavefront"])
+def test_index_outputs_bit_exact(problems, name, smoother):
+    pr = problems[name]
+    _check_index_outputs(pr.P, pr.A, pr.known, smoother)
+
+
+@pytest.mark.parametrize("name", golden_util.NAMES)
+def test_index_outputs_golden(name):
+    g = golden_util.load(name)
+    s, _ = _check_index_outputs(g["P"], g["A"], g["known"], "multicolour")
+    assert np.array_equal(s.unknown, g["unknown"])
+
+
+def test_known_edge_cases(problems):
+    pr = problems["sphere"]
+    # empty known list (fixed variant with nothing fixed), repeated and unsorted indices
+    for known in (np.zeros(0, dtype=np.int32), np.array([9, 2, 2, 40, 0], dtype=np.int32)):
+        _check_index_outputs(pr.P, pr.A, known, "multicolour")
+    with pytest.raises(SmgError):
+        Solver(device="none").set_hierarchy(pr.P).precompute(pr.A, np.array([pr.n], dtype=np.int32))
+
+
+@pytest.mark.parametrize("smoother", ["multicolour", "wavefront"])
+def test_smoother_schedule_is_valid(problems, smoother):
+    """Rows of one phase never touch each other through a non-zero-capable entry; the
+    wavefront schedule additionally respects the lexicographic order."""
+    pr = problems["grid"]
+    s = Solver(smoother=smoother, device="none").set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    ora = Oracle(pr.P).precompute(pr.A, pr.known)
+    for lv in range(pr.nlev):
+        nph, phase = s.phases(lv)
+        A = ora.matrix(lv, "A").tocoo()
+        live = (A.data != 0) & (A.row != A.col)
+        r, c = A.row[live], A.col[live]
+        assert not np.any(phase[r] == phase[c])
+        assert phase.min() == 0 and phase.max() == nph - 1
+        if smoother == "wavefront":
+            lower = c < r  # row r reads the already-updated u[c]
+            assert np.all(phase[c[lower]] < phase[r[lower]])
+        st = s.level_stats(lv)
+        assert st["nnz"] <= st["nnz_ref"] and st["padded"] >= st["nnz"]
+
+
+def test_hierarchy_validation(problems):
+    pr = problems["sphere_pad"]
+    with pytest.raises(SmgError) as e:
+        Solver(device="none").set_hierarchy([])
+    assert e.value.status == 3  # SMG_E_NLEVELS: the nLvs == 1 mis-solve is not replicated
+    with pytest.raises(SmgError):
+        Solver(device="none").set_hierarchy(pr.P).precompute(pr.A[:-1][:, :-1], None)
+    with pytest.raises(SmgError):
+        Solver(device="none").precompute(pr.A, pr.known)  # no hierarchy yet
