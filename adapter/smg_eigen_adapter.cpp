@@ -1,0 +1,329 @@
+// smg_eigen_adapter.cpp -- drop-in replacement translation unit for the reference's
+//     src/min_quad_with_fixed_mg.cpp   and   src/mg_VCycle.cpp .
+//
+// It includes the reference's OWN, UNMODIFIED headers (min_quad_with_fixed_mg.h,
+// mg_VCycle.h, mg_data.h) and defines exactly the functions they declare, so the
+// examples (03_mg_solver/main.cpp:71,75, 04_mg_solver_nobd/main.cpp:100,105,
+// 05_example_mean_curvature_flow/main.cpp:74,76, 06_.../implicit_euler_mg_balloon.h:75-76)
+// compile and link unchanged; all arithmetic happens in libsmg.so (include/smg.h) on the
+// GPU.  Build: remove the two reference .cpp files from the example's source glob, add
+// this file, `-I<repo>/include`, link `-lsmg`.
+//
+// Host code stays C++/Eigen as the reference's; Eigen 3.3.7 is NOT available in the image
+// this repository is developed in, so this file is compile-checked there only against
+// a declaration-level Eigen stub (tests/eigen_stub); it has not been linked against the
+// real Eigen yet (stated in DESIGN.md).
+//
+// Semantics kept (reference file:line):
+//   * precompute mutates `data` (n, known, unknown) and `mg` is left untouched unless
+//     SMG_MIRROR_TO_HOST=1, in which case mg[lv].A / A_diag / P / PT and data.LHS / Auk are
+//     copied back from the device (min_quad_with_fixed_mg.cpp:156-246);
+//   * the SimplicialLDLT argument is accepted and ignored (the coarse factorisation lives
+//     on the device);
+//   * solve prints one residual per iteration and "residual norm: ..." like the reference
+//     (cpp:334,349) unless SMG_QUIET=1; r_his / return value follow cpp:330-360 exactly.
+#include <min_quad_with_fixed_mg.h>
+#include <mg_VCycle.h>
+
+#include <smg.h>
+
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+namespace {
+
+struct HandleDeleter {
+  void operator()(smg_handle* h) const { smg_destroy(h); }
+};
+using HandlePtr = std::unique_ptr<smg_handle, HandleDeleter>;
+
+// The reference's structs have no room for a device handle and must stay unmodified,
+// so handles are looked up by the address of the caller's objects: the hierarchy
+// vector `mg` (what mg_VCycle & co. receive) and the solver `data` struct.
+std::map<const void*, std::shared_ptr<smg_handle>>& registry() {
+  static std::map<const void*, std::shared_ptr<smg_handle>> r;
+  return r;
+}
+
+bool env_flag(const char* name) {
+  const char* v = std::getenv(name);
+  return v && *v && *v != '0';
+}
+
+void check(smg_handle* h, int rc, const char* what) {
+  if (rc != SMG_OK)
+    throw std::runtime_error(std::string(what) + ": " + smg_status_string(rc) + " (" +
+                             smg_last_error(h) + ")");
+}
+
+smg_handle* lookup(const void* key) {
+  auto it = registry().find(key);
+  if (it == registry().end())
+    throw std::runtime_error("smg adapter: min_quad_with_fixed_mg_precompute has not been called");
+  return it->second.get();
+}
+
+Eigen::SparseMatrix<double> fetch_matrix(smg_handle* h, int lv, int which) {
+  int rows = 0, cols = 0, nnz = 0;
+  check(h, smg_matrix_dims(h, lv, which, &rows, &cols, &nnz), "smg_matrix_dims");
+  Eigen::SparseMatrix<double> M(rows, cols);
+  M.resizeNonZeros(nnz);
+  check(h, smg_matrix_copy(h, lv, which, M.outerIndexPtr(), M.innerIndexPtr(), M.valuePtr()),
+        "smg_matrix_copy");
+  return M;
+}
+
+void precompute_impl(const Eigen::SparseMatrix<double>& A_in, const Eigen::VectorXi* known,
+                     min_quad_with_fixed_mg_data& data, std::vector<mg_data>& mg) {
+  smg_options opt;
+  smg_default_options(&opt);
+  if (const char* s = std::getenv("SMG_SMOOTHER")) opt.smoother = std::atoi(s);
+  opt.verbose = env_flag("SMG_QUIET") ? 0 : 1;
+  smg_handle* raw = nullptr;
+  check(nullptr, smg_create(&raw, &opt), "smg_create");
+  std::shared_ptr<smg_handle> h(raw, HandleDeleter());
+
+  // hierarchy as mg_precompute left it (src/mg_precompute.cpp:71-77): mg[lv].P_full
+  const int nlev = static_cast<int>(mg.size());
+  std::vector<Eigen::SparseMatrix<double>> P(nlev > 0 ? nlev - 1 : 0);
+  std::vector<int> n_rows(nlev);
+  std::vector<const int*> cp, ri;
+  std::vector<const double*> vv;
+  for (int lv = 1; lv < nlev; lv++) {
+    P[lv - 1] = mg[lv].P_full;
+    P[lv - 1].makeCompressed();
+    if (lv == 1) n_rows[0] = static_cast<int>(P[0].rows());
+    n_rows[lv] = static_cast<int>(P[lv - 1].cols());
+    cp.push_back(P[lv - 1].outerIndexPtr());
+    ri.push_back(P[lv - 1].innerIndexPtr());
+    vv.push_back(P[lv - 1].valuePtr());
+  }
+  check(h.get(), smg_set_hierarchy(h.get(), nlev, n_rows.data(), cp.data(), ri.data(), vv.data()),
+        "smg_set_hierarchy");
+
+  Eigen::SparseMatrix<double> A = A_in;
+  A.makeCompressed();
+  const int n = static_cast<int>(A.rows());
+  check(h.get(),
+        smg_precompute(h.get(), n, A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(),
+                       known ? known->data() : nullptr, known ? static_cast<int>(known->size()) : -1),
+        "smg_precompute");
+
+  data.n = n;
+  data.unknown.resize(smg_num_unknown(h.get()));
+  check(h.get(), smg_get_unknown(h.get(), data.unknown.data()), "smg_get_unknown");
+  if (known) data.known = *known;
+  else data.known.resize(0);
+  if (env_flag("SMG_MIRROR_TO_HOST")) {
+    data.LHS = fetch_matrix(h.get(), 0, SMG_MAT_LHS);
+    if (known) data.Auk = fetch_matrix(h.get(), 0, SMG_MAT_AUK);
+    for (int lv = 0; lv < nlev; lv++) {
+      mg[lv].A = fetch_matrix(h.get(), lv, SMG_MAT_A);
+      mg[lv].A_diag = mg[lv].A.diagonal();
+      if (lv >= 1) {
+        mg[lv].P = fetch_matrix(h.get(), lv, SMG_MAT_P);
+        mg[lv].PT = fetch_matrix(h.get(), lv, SMG_MAT_PT);
+      }
+    }
+  }
+  registry()[&data] = h;
+  registry()[&mg] = h;
+}
+
+template <typename DerivedRHS, typename DerivedZ0, typename DerivedZ>
+bool solve_impl(const min_quad_with_fixed_mg_data& data,
+                const Eigen::PlainObjectBase<DerivedRHS>& RHS, const double* known_val,
+                const Eigen::PlainObjectBase<DerivedZ0>& z0, double tolerance, int maxIter,
+                Eigen::PlainObjectBase<DerivedZ>& z, std::vector<double>& r_his) {
+  smg_handle* h = lookup(&data);
+  const int k = static_cast<int>(RHS.cols());
+  // Eigen dense objects are column-major with leading dimension rows(): exactly the ABI's layout
+  z.resize(z0.rows(), z0.cols());
+  std::vector<double> his(maxIter > 0 ? maxIter : 1);
+  int n_his = 0, converged = 0;
+  check(h,
+        smg_solve(h, RHS.derived().data(), known_val, z0.derived().data(), k, tolerance, maxIter,
+                  z.derived().data(), his.data(), &n_his, &converged),
+        "smg_solve");
+  r_his.insert(r_his.end(), his.begin(), his.begin() + n_his);  // the reference push_back's (cpp:335)
+  return converged != 0;
+}
+
+}  // namespace
+
+// ---- min_quad_with_fixed_mg.h -----------------------------------------------------
+void min_quad_with_fixed_mg_precompute(const Eigen::SparseMatrix<double>& A,
+                                       min_quad_with_fixed_mg_data& data, std::vector<mg_data>& mg,
+                                       Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/) {
+  precompute_impl(A, nullptr, data, mg);
+}
+
+void min_quad_with_fixed_mg_precompute(const Eigen::SparseMatrix<double>& A,
+                                       const Eigen::VectorXi& known,
+                                       min_quad_with_fixed_mg_data& data, std::vector<mg_data>& mg,
+                                       Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/) {
+  precompute_impl(A, &known, data, mg);
+}
+
+// variant without fixed values: maxIter / tolerance defaults of cpp:53-78
+template <typename DerivedRHS, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& solver,
+                                  std::vector<mg_data>& mg, Eigen::PlainObjectBase<DerivedZ>& z,
+                                  std::vector<double>& r_his) {
+  return min_quad_with_fixed_mg_solve(data, RHS, z0, solver, 1e-3, mg, z, r_his);
+}
+
+template <typename DerivedRHS, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& solver,
+                                  const double& tolerance, std::vector<mg_data>& mg,
+                                  Eigen::PlainObjectBase<DerivedZ>& z, std::vector<double>& r_his) {
+  return min_quad_with_fixed_mg_solve(data, RHS, z0, solver, tolerance, 20, mg, z, r_his);
+}
+
+template <typename DerivedRHS, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/,
+                                  const double& tolerance, const int& maxIter,
+                                  std::vector<mg_data>& /*mg*/, Eigen::PlainObjectBase<DerivedZ>& z,
+                                  std::vector<double>& r_his) {
+  return solve_impl(data, RHS, nullptr, z0, tolerance, maxIter, z, r_his);
+}
+
+// variant with fixed values: defaults of cpp:259-286
+template <typename DerivedRHS, typename DerivedKnownVal, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedKnownVal>& known_val,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& solver,
+                                  std::vector<mg_data>& mg, Eigen::PlainObjectBase<DerivedZ>& z,
+                                  std::vector<double>& r_his) {
+  return min_quad_with_fixed_mg_solve(data, RHS, known_val, z0, solver, 1e-3, mg, z, r_his);
+}
+
+template <typename DerivedRHS, typename DerivedKnownVal, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedKnownVal>& known_val,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& solver,
+                                  const double& tolerance, std::vector<mg_data>& mg,
+                                  Eigen::PlainObjectBase<DerivedZ>& z, std::vector<double>& r_his) {
+  return min_quad_with_fixed_mg_solve(data, RHS, known_val, z0, solver, tolerance, 20, mg, z, r_his);
+}
+
+template <typename DerivedRHS, typename DerivedKnownVal, typename DerivedZ0, typename DerivedZ>
+bool min_quad_with_fixed_mg_solve(const min_quad_with_fixed_mg_data& data,
+                                  const Eigen::PlainObjectBase<DerivedRHS>& RHS,
+                                  const Eigen::PlainObjectBase<DerivedKnownVal>& known_val,
+                                  const Eigen::PlainObjectBase<DerivedZ0>& z0,
+                                  const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/,
+                                  const double& tolerance, const int& maxIter,
+                                  std::vector<mg_data>& /*mg*/, Eigen::PlainObjectBase<DerivedZ>& z,
+                                  std::vector<double>& r_his) {
+  return solve_impl(data, RHS, known_val.derived().data(), z0, tolerance, maxIter, z, r_his);
+}
+
+// ---- mg_VCycle.h ---------------------------------------------------------------------
+template <typename DeriveddB, typename DeriveddU>
+void mg_VCycle(const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/,
+               const Eigen::PlainObjectBase<DeriveddB>& B, const int& preRelaxIter,
+               const int& postRelaxIter, const int lv, Eigen::PlainObjectBase<DeriveddU>& u,
+               std::vector<mg_data>& mg) {
+  smg_handle* h = lookup(&mg);
+  check(h, smg_vcycle(h, lv, preRelaxIter, postRelaxIter, B.derived().data(), u.derived().data(),
+                      static_cast<int>(B.cols())), "smg_vcycle");
+}
+
+template <typename DeriveddU, typename DeriveddAU>
+void A(const Eigen::PlainObjectBase<DeriveddU>& u, const std::vector<mg_data>& mg, const int& lv,
+       Eigen::PlainObjectBase<DeriveddAU>& Au) {
+  smg_handle* h = lookup(&mg);
+  Au.resize(u.rows(), u.cols());
+  check(h, smg_apply_A(h, lv, u.derived().data(), Au.derived().data(), static_cast<int>(u.cols())),
+        "smg_apply_A");
+}
+
+template <typename DeriveddX, typename DeriveddRX>
+void restrict(const Eigen::PlainObjectBase<DeriveddX>& x, const std::vector<mg_data>& mg,
+              const int& lv, Eigen::PlainObjectBase<DeriveddRX>& Rx) {
+  smg_handle* h = lookup(&mg);
+  Rx.resize(smg_level_rows(h, lv + 1), x.cols());
+  check(h, smg_restrict(h, lv, x.derived().data(), Rx.derived().data(), static_cast<int>(x.cols())),
+        "smg_restrict");
+}
+
+template <typename DerivedX, typename DerivedPX>
+void prolong(const Eigen::PlainObjectBase<DerivedX>& x, const std::vector<mg_data>& mg, const int& lv,
+             Eigen::PlainObjectBase<DerivedPX>& Px) {
+  smg_handle* h = lookup(&mg);
+  Px.resize(smg_level_rows(h, lv), x.cols());
+  check(h, smg_prolong(h, lv, x.derived().data(), Px.derived().data(), static_cast<int>(x.cols())),
+        "smg_prolong");
+}
+
+// dead code in the reference (verbose is hard-wired to false, mg_VCycle.cpp:20,103)
+template <typename DerivedB, typename DerivedU>
+void printErrorNorm(const int, const std::string&, const std::vector<mg_data>&,
+                    const Eigen::PlainObjectBase<DerivedB>&, const Eigen::PlainObjectBase<DerivedU>&,
+                    const bool) {}
+
+template <typename DerivedB, typename DerivedU>
+void relax(const Eigen::PlainObjectBase<DerivedB>& B, const int& lv, const int& iters,
+           Eigen::PlainObjectBase<DerivedU>& u, std::vector<mg_data>& mg) {
+  smg_handle* h = lookup(&mg);
+  check(h, smg_relax(h, lv, iters, B.derived().data(), u.derived().data(), static_cast<int>(B.cols())),
+        "smg_relax");
+}
+
+template <typename DerivedB, typename DerivedU>
+void coarseSolve(const Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>& /*solver*/,
+                 const Eigen::PlainObjectBase<DerivedB>& B, const int& /*lv*/,
+                 Eigen::PlainObjectBase<DerivedU>& u, std::vector<mg_data>& mg) {
+  smg_handle* h = lookup(&mg);
+  check(h, smg_coarse_solve(h, B.derived().data(), u.derived().data(), static_cast<int>(B.cols())),
+        "smg_coarse_solve");
+}
+
+// ---- explicit instantiations: the set the reference provides (min_quad_with_fixed_mg.cpp:
+// 363-373, mg_VCycle.cpp:203) plus the MatrixXd V-cycle the 05 example reaches implicitly
+using Eigen::MatrixXd;
+using Eigen::VectorXd;
+using LDLT = Eigen::SimplicialLDLT<Eigen::SparseMatrix<double>>;
+#define SMG_PB(T) Eigen::PlainObjectBase<T>
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&, const LDLT&,
+    std::vector<mg_data>&, SMG_PB(VectorXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&, const LDLT&,
+    const double&, std::vector<mg_data>&, SMG_PB(VectorXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<MatrixXd, MatrixXd, MatrixXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(MatrixXd)&, const SMG_PB(MatrixXd)&, const LDLT&,
+    const double&, std::vector<mg_data>&, SMG_PB(MatrixXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&,
+    const SMG_PB(VectorXd)&, const LDLT&, std::vector<mg_data>&, SMG_PB(VectorXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&,
+    const SMG_PB(VectorXd)&, const LDLT&, const double&, std::vector<mg_data>&, SMG_PB(VectorXd)&,
+    std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<MatrixXd, MatrixXd, MatrixXd, MatrixXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(MatrixXd)&, const SMG_PB(MatrixXd)&,
+    const SMG_PB(MatrixXd)&, const LDLT&, const double&, std::vector<mg_data>&, SMG_PB(MatrixXd)&,
+    std::vector<double>&);
+template void mg_VCycle<VectorXd, VectorXd>(const LDLT&, const SMG_PB(VectorXd)&, const int&, const int&,
+                                            const int, SMG_PB(VectorXd)&, std::vector<mg_data>&);
+template void mg_VCycle<MatrixXd, MatrixXd>(const LDLT&, const SMG_PB(MatrixXd)&, const int&, const int&,
+                                            const int, SMG_PB(MatrixXd)&, std::vector<mg_data>&);
+#undef SMG_PB

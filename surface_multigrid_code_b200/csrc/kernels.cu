@@ -19,6 +19,20 @@ namespace smg {
 namespace {
 
 constexpr int kBlock = 256;  // threads per CTA = 8 slices
+constexpr int kPre = 8;      // matrix entries per row prefetched into registers
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// Every hot-path kernel is launched with programmatic stream serialisation: it may
+// start while its predecessor is still running.  Before `pdl_wait()` a kernel only
+// touches data that no kernel of a solve ever writes (matrix structure / values,
+// diagonal); everything mutable (b, u, r) is read and written after the wait, which
+// guarantees the predecessor has completed and its writes are visible.  Mutable
+// vectors are read with ld.global.cg (L2 is the coherence point; an SM's L1 may hold
+// lines cached by CTAs of the still-running predecessor).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ double ld_stream_f64(const double* p) {
   double v;
@@ -30,71 +44,116 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ double ld_vec(const double* p) {  // mutable vector data
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// sum[q] (+)= sum over the row's stored entries of val * x[col + q*ldx], entries in
-// storage order (ascending original index), products and sums rounded separately.
-template <int K, bool SKIP_DIAG>
-__device__ __forceinline__ void row_accumulate(const int* __restrict__ col,
-                                               const double* __restrict__ val, int base, int w,
-                                               int lane, int row, const double* x, int ldx,
-                                               double (&sum)[K]) {
-  const int* cp = col + base + lane;
-  const double* vp = val + base + lane;
-  int j = 0;
-  for (; j + 4 <= w; j += 4) {
-    int c[4];
-    double v[4];
+bool g_use_pdl = true;
+
+template <class... KArgs, class... Args>
+void launch_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// One SELL row held by one thread: the first kPre entries live in registers (loaded
+// before the PDL wait), the rest (rows longer than kPre) are streamed afterwards.
+struct RowHead {
+  int base, w, lane;
+  int c[kPre];
+  double v[kPre];
+};
+
+__device__ __forceinline__ void row_head_load(RowHead& h, int row, const int* __restrict__ slice_ptr,
+                                              const int* __restrict__ col,
+                                              const double* __restrict__ val) {
+  const int s = row >> 5;
+  h.lane = row & 31;
+  h.base = slice_ptr[s];
+  h.w = (slice_ptr[s + 1] - h.base) >> 5;
+  const int* cp = col + h.base + h.lane;
+  const double* vp = val + h.base + h.lane;
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-      c[t] = ld_stream_s32(cp + (j + t) * 32);
-      v[t] = ld_stream_f64(vp + (j + t) * 32);
+  for (int t = 0; t < kPre; t++)
+    if (t < h.w) {
+      h.c[t] = ld_stream_s32(cp + t * 32);
+      h.v[t] = ld_stream_f64(vp + t * 32);
     }
-    double xv[4][K];
+}
+
+// sum[q] += sum over the row's stored entries of val * x[col + q*ldx], entries in
+// storage order (ascending original index), products and sums rounded separately
+// (no FMA: the reference build has none).
+template <int K, bool SKIP_DIAG>
+__device__ __forceinline__ void row_accumulate(const RowHead& h, int row, const int* __restrict__ col,
+                                               const double* __restrict__ val, const double* x,
+                                               int ldx, double (&sum)[K]) {
+  double xv[kPre][K];
 #pragma unroll
-    for (int t = 0; t < 4; t++)
+  for (int t = 0; t < kPre; t++)
+    if (t < h.w && !(SKIP_DIAG && h.c[t] == row)) {
 #pragma unroll
-      for (int q = 0; q < K; q++) xv[t][q] = x[c[t] + (size_t)q * ldx];
+      for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + h.c[t] + (size_t)q * ldx);
+    }
 #pragma unroll
-    for (int t = 0; t < 4; t++)
+  for (int t = 0; t < kPre; t++)
+    if (t < h.w && !(SKIP_DIAG && h.c[t] == row)) {
 #pragma unroll
-      for (int q = 0; q < K; q++) {
-        const double s = __dadd_rn(sum[q], __dmul_rn(v[t], xv[t][q]));
-        sum[q] = (SKIP_DIAG && c[t] == row) ? sum[q] : s;
-      }
-  }
-  for (; j < w; j++) {
+      for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(h.v[t], xv[t][q]));
+    }
+  const int* cp = col + h.base + h.lane;
+  const double* vp = val + h.base + h.lane;
+  for (int j = kPre; j < h.w; j++) {
     const int c = ld_stream_s32(cp + j * 32);
     const double v = ld_stream_f64(vp + j * 32);
+    if (SKIP_DIAG && c == row) continue;
 #pragma unroll
-    for (int q = 0; q < K; q++) {
-      const double s = __dadd_rn(sum[q], __dmul_rn(v, x[c + (size_t)q * ldx]));
-      sum[q] = (SKIP_DIAG && c == row) ? sum[q] : s;
-    }
+    for (int q = 0; q < K; q++)
+      sum[q] = __dadd_rn(sum[q], __dmul_rn(v, ld_vec(x + c + (size_t)q * ldx)));
   }
 }
 
-enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2 };
+enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3 };
 
+// y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
 template <int K, int MODE>
 __global__ void __launch_bounds__(kBlock)
 sell_apply_kernel(int nrows, const int* __restrict__ slice_ptr, const int* __restrict__ col,
-                  const double* __restrict__ val, const double* __restrict__ x, int ldx,
-                  const double* __restrict__ b, double* __restrict__ y, int ldy) {
+                  const double* __restrict__ val, const double* x, int ldx, const double* b,
+                  double* y, int ldy, double* z) {
+  pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
-  if (row >= nrows) return;
-  const int s = row >> 5, lane = row & 31;
-  const int base = slice_ptr[s];
-  const int w = (slice_ptr[s + 1] - base) >> 5;
+  const bool active = row < nrows;
+  RowHead h;
+  h.w = 0;
+  if (active) row_head_load(h, row, slice_ptr, col, val);
+  pdl_wait();
+  if (!active) return;
   double sum[K];
 #pragma unroll
   for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, false>(col, val, base, w, lane, row, x, ldx, sum);
+  row_accumulate<K, false>(h, row, col, val, x, ldx, sum);
 #pragma unroll
   for (int q = 0; q < K; q++) {
     const size_t o = row + (size_t)q * ldy;
     if (MODE == MODE_SPMV) y[o] = sum[q];
-    if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(b[o], sum[q]);
-    if (MODE == MODE_ADD) y[o] = __dadd_rn(y[o], sum[q]);
+    if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(ld_vec(b + o), sum[q]);
+    if (MODE == MODE_ADD) y[o] = __dadd_rn(ld_vec(y + o), sum[q]);
+    if (MODE == MODE_SPMV_ZERO) {
+      y[o] = sum[q];
+      z[o] = 0.0;
+    }
   }
 }
 
@@ -102,21 +161,23 @@ template <int K>
 __global__ void __launch_bounds__(kBlock)
 sell_residual_norm_kernel(int nrows, const int* __restrict__ slice_ptr,
                           const int* __restrict__ col, const double* __restrict__ val,
-                          const double* __restrict__ x, const double* __restrict__ b, int ld,
-                          double* __restrict__ partial) {
+                          const double* x, const double* b, int ld, double* __restrict__ partial) {
+  pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
+  const bool active = row < nrows;
+  RowHead h;
+  h.w = 0;
+  if (active) row_head_load(h, row, slice_ptr, col, val);
+  pdl_wait();
   double d2 = 0.0;
-  if (row < nrows) {
-    const int s = row >> 5, lane = row & 31;
-    const int base = slice_ptr[s];
-    const int w = (slice_ptr[s + 1] - base) >> 5;
+  if (active) {
     double sum[K];
 #pragma unroll
     for (int q = 0; q < K; q++) sum[q] = 0.0;
-    row_accumulate<K, false>(col, val, base, w, lane, row, x, ld, sum);
+    row_accumulate<K, false>(h, row, col, val, x, ld, sum);
 #pragma unroll
     for (int q = 0; q < K; q++) {
-      const double d = __dsub_rn(b[row + (size_t)q * ld], sum[q]);
+      const double d = __dsub_rn(ld_vec(b + row + (size_t)q * ld), sum[q]);
       d2 += d * d;
     }
   }
@@ -135,10 +196,12 @@ sell_residual_norm_kernel(int nrows, const int* __restrict__ slice_ptr,
 }
 
 __global__ void __launch_bounds__(1024)
-reduce_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+reduce_partials_kernel(const double* partial, int n, double* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double sm[1024];
   double t = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) t += partial[i];
+  for (int i = threadIdx.x; i < n; i += 1024) t += ld_vec(partial + i);
   sm[threadIdx.x] = t;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
@@ -155,28 +218,35 @@ template <int K>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_phase_kernel(int row0, int ps, int pe, const int* __restrict__ slice_ptr,
                      const int* __restrict__ col, const double* __restrict__ val,
-                     const double* __restrict__ diag, const double* __restrict__ b, double* u,
-                     int ld) {
+                     const double* __restrict__ diag, const double* b, double* u, int ld) {
+  pdl_launch_dependents();
   const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
-  if (row < ps || row >= pe) return;
-  const int s = row >> 5, lane = row & 31;
-  const int base = slice_ptr[s];
-  const int w = (slice_ptr[s + 1] - base) >> 5;
+  const bool active = row >= ps && row < pe;
+  RowHead h;
+  h.w = 0;
+  double d = 1.0;
+  if (active) {
+    row_head_load(h, row, slice_ptr, col, val);
+    d = ld_stream_f64(diag + row);
+  }
+  pdl_wait();
+  if (!active) return;
   double sum[K];
 #pragma unroll
   for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, true>(col, val, base, w, lane, row, u, ld, sum);
-  const double d = diag[row];
+  row_accumulate<K, true>(h, row, col, val, u, ld, sum);
 #pragma unroll
   for (int q = 0; q < K; q++) {
     const size_t o = row + (size_t)q * ld;
-    u[o] = __ddiv_rn(__dsub_rn(b[o], sum[q]), d);
+    u[o] = __ddiv_rn(__dsub_rn(ld_vec(b + o), sum[q]), d);
   }
 }
 
 inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 }  // namespace
+
+void set_pdl_enabled(bool on) { g_use_pdl = on; }
 
 #define SMG_DISPATCH_K(k, ...)                 \
   switch (k) {                                 \
@@ -191,24 +261,32 @@ void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, doub
   if (M.nrows <= 0) return;
   const double* v = use_valT ? M.valT : M.val;
   const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_SPMV><<<g, kBlock, 0, st>>>(
-                        M.nrows, M.slice_ptr, M.col, v, x, ldx, nullptr, y, ldy)));
+  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_SPMV>, g, kBlock, st, M.nrows,
+                                  M.slice_ptr, M.col, v, x, ldx, nullptr, y, ldy, nullptr));
+}
+
+void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, double* z, int ldy,
+                      int k, cudaStream_t st) {
+  if (M.nrows <= 0) return;
+  const int g = blocks_for(M.nrows, kBlock);
+  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_SPMV_ZERO>, g, kBlock, st, M.nrows,
+                                  M.slice_ptr, M.col, M.val, x, ldx, nullptr, y, ldy, z));
 }
 
 void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
                      cudaStream_t st) {
   if (M.nrows <= 0) return;
   const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_RESIDUAL><<<g, kBlock, 0, st>>>(
-                        M.nrows, M.slice_ptr, M.col, M.valT, x, ld, b, r, ld)));
+  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_RESIDUAL>, g, kBlock, st, M.nrows,
+                                  M.slice_ptr, M.col, M.valT, x, ld, b, r, ld, nullptr));
 }
 
 void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, int ldu, int k,
                         cudaStream_t st) {
   if (M.nrows <= 0) return;
   const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, (sell_apply_kernel<K, MODE_ADD><<<g, kBlock, 0, st>>>(
-                        M.nrows, M.slice_ptr, M.col, M.val, x, ldx, nullptr, u, ldu)));
+  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_ADD>, g, kBlock, st, M.nrows,
+                                  M.slice_ptr, M.col, M.val, x, ldx, nullptr, u, ldu, nullptr));
 }
 
 int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, kBlock); }
@@ -216,9 +294,9 @@ int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, k
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st) {
   const int g = residual_norm_blocks(M.nrows);
-  SMG_DISPATCH_K(k, (sell_residual_norm_kernel<K><<<g, kBlock, 0, st>>>(
-                        M.nrows, M.slice_ptr, M.col, M.valT, x, b, ld, scratch)));
-  reduce_partials_kernel<<<1, 1024, 0, st>>>(scratch, g, out);
+  SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K>, g, kBlock, st, M.nrows,
+                                  M.slice_ptr, M.col, M.valT, x, b, ld, scratch));
+  launch_kernel(reduce_partials_kernel, 1, 1024, st, scratch, g, out);
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
@@ -226,8 +304,8 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
   if (pe <= ps) return;
   const int row0 = ps & ~31;
   const int g = blocks_for(pe - row0, kBlock);
-  SMG_DISPATCH_K(k, (sell_gs_phase_kernel<K><<<g, kBlock, 0, st>>>(
-                        row0, ps, pe, M.slice_ptr, M.col, M.val, diag, b, u, ld)));
+  SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K>, g, kBlock, st, row0, ps, pe,
+                                  M.slice_ptr, M.col, M.val, diag, b, u, ld));
 }
 
 // ---------------------------------------------------------------------------
@@ -345,25 +423,43 @@ __global__ void symmetrize_lower_kernel(double* D, int n) {
 // read as the contiguous column i.
 template <int K>
 __global__ void __launch_bounds__(kBlock)
-dense_symv_add_kernel(const double* __restrict__ Ainv, const double* __restrict__ b, double* u,
-                      int n) {
+dense_symv_add_kernel(const double* __restrict__ Ainv, const double* b, double* u, int n) {
+  pdl_launch_dependents();
   const int i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  if (i >= n) return;
   const int lane = threadIdx.x & 31;
-  const double* a = Ainv + (size_t)i * n;
+  // the inverse is immutable during a solve: the first chunk of the row is fetched
+  // before the PDL wait
+  constexpr int kAhead = 4;
+  double ahead[kAhead];
+  const double* a = Ainv + (size_t)(i < n ? i : 0) * n;
+#pragma unroll
+  for (int t = 0; t < kAhead; t++) {
+    const int j = lane + 32 * t;
+    ahead[t] = (i < n && j < n) ? ld_stream_f64(a + j) : 0.0;
+  }
+  pdl_wait();
+  if (i >= n) return;
   double acc[K];
 #pragma unroll
   for (int q = 0; q < K; q++) acc[q] = 0.0;
-  for (int j = lane; j < n; j += 32) {
+#pragma unroll
+  for (int t = 0; t < kAhead; t++) {
+    const int j = lane + 32 * t;
+    if (j < n) {
+#pragma unroll
+      for (int q = 0; q < K; q++) acc[q] += ahead[t] * ld_vec(b + j + (size_t)q * n);
+    }
+  }
+  for (int j = lane + 32 * kAhead; j < n; j += 32) {
     const double aij = ld_stream_f64(a + j);
 #pragma unroll
-    for (int q = 0; q < K; q++) acc[q] += aij * b[j + (size_t)q * n];
+    for (int q = 0; q < K; q++) acc[q] += aij * ld_vec(b + j + (size_t)q * n);
   }
 #pragma unroll
   for (int q = 0; q < K; q++) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
-    if (lane == 0) u[i + (size_t)q * n] = u[i + (size_t)q * n] + acc[q];
+    if (lane == 0) u[i + (size_t)q * n] = ld_vec(u + i + (size_t)q * n) + acc[q];
   }
 }
 
@@ -426,6 +522,8 @@ __global__ void permute_out_kernel(const double* __restrict__ in, const int* __r
 }
 
 __global__ void fill_kernel(double* p, double v, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -475,7 +573,7 @@ void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n
                            cudaStream_t st) {
   if (n <= 0) return;
   const int g = blocks_for(n, kBlock / 32);
-  SMG_DISPATCH_K(k, (dense_symv_add_kernel<K><<<g, kBlock, 0, st>>>(Ainv, b, u, n)));
+  SMG_DISPATCH_K(k, launch_kernel(dense_symv_add_kernel<K>, g, kBlock, st, Ainv, b, u, n));
 }
 void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
                           int n_known, const int* g, const int* auk_ptr, const int* auk_q,
@@ -504,7 +602,7 @@ void launch_permute_out(const double* in, const int* perm, double* out, int n, i
   if (n > 0) permute_out_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
 }
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
-  if (n > 0) fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, v, n);
+  if (n > 0) launch_kernel(fill_kernel, blocks_for(n, 256), 256, st, p, v, n);
 }
 
 }  // namespace smg

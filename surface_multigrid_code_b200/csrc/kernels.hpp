@@ -24,6 +24,11 @@ constexpr int kMaxK = 4;  // right-hand sides handled per kernel pass
 // y = M x  (y: nrows x k, ldy; x: ldx)
 void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
                  int k, cudaStream_t st);
+// y = M x and z = 0 (z has the shape of y): restriction fused with zeroing the coarse guess
+void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, double* z, int ldy,
+                      int k, cudaStream_t st);
+// programmatic dependent launch of the hot-path kernels (default on)
+void set_pdl_enabled(bool on);
 // r = b - M x
 void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
                      cudaStream_t st);

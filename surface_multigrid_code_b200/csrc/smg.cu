@@ -26,6 +26,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -265,15 +266,17 @@ void apply_A_device(smg_handle* h, int l, const double* u, double* y, int k) {
   }
 }
 
-// x on level l (fine), y on level l+1
-void restrict_device(smg_handle* h, int l, const double* x, double* y, int k) {
+// x on level l (fine), y on level l+1; zero != nullptr: also zero[...] = 0 (same shape as y)
+void restrict_device(smg_handle* h, int l, const double* x, double* y, int k, double* zero = nullptr) {
   LevelDev& F = h->lv[l];
   LevelDev& C = h->lv[l + 1];
   if (C.n <= 0) return;
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
-    smg::launch_spmv(C.sellPT.view(), false, x + static_cast<size_t>(k0) * F.n, F.n,
-                     y + static_cast<size_t>(k0) * C.n, C.n, kk, h->stream);
+    const double* xx = x + static_cast<size_t>(k0) * F.n;
+    const size_t oc = static_cast<size_t>(k0) * C.n;
+    if (zero) smg::launch_spmv_zero(C.sellPT.view(), xx, F.n, y + oc, zero + oc, C.n, kk, h->stream);
+    else smg::launch_spmv(C.sellPT.view(), false, xx, F.n, y + oc, C.n, kk, h->stream);
     h->launches++;
   }
 }
@@ -304,12 +307,6 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
   }
 }
 
-void fill_device(smg_handle* h, double* p, double v, int64_t n) {
-  if (n <= 0) return;
-  smg::launch_fill(p, v, n, h->stream);
-  h->launches++;
-}
-
 // mg_VCycle (src/mg_VCycle.cpp:3-59) unrolled over levels; operates on the resident
 // work vectors lv[l].b / .u of levels l >= lv0.
 void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
@@ -319,8 +316,7 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     LevelDev& C = h->lv[l + 1];
     relax_device(h, l, pre, L.b.p, L.u.p, k);              // :36
     residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
-    restrict_device(h, l, L.r.p, C.b.p, k);                // :44
-    fill_device(h, C.u.p, 0.0, static_cast<int64_t>(C.n) * k);  // :46-47
+    restrict_device(h, l, L.r.p, C.b.p, k, C.u.p);         // :44 and uc = 0 (:46-47), fused
   }
   coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
   for (int l = last - 1; l >= lv0; l--) {
@@ -756,6 +752,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
     return SMG_E_CUDA;
   }
   h->device = dev;
+  if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 64 * sizeof(double)) != cudaSuccess) {
     smg_destroy(h);
