@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmg.so")
+# SMG_LIB_PATH: load another build of the same library (profiling experiments only)
+LIB_PATH = os.environ.get("SMG_LIB_PATH") or os.path.join(_HERE, "libsmg.so")
 
 SMG_DEVICE_CURRENT = -1
 SMG_DEVICE_NONE = -2

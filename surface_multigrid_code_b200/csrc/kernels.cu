@@ -51,13 +51,15 @@ __device__ __forceinline__ double ld_vec(const double* p) {  // mutable vector d
 }
 
 bool g_use_pdl = true;
+bool g_use_tma = true;
 
 template <class... KArgs, class... Args>
-void launch_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+void launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                   Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -67,83 +69,166 @@ void launch_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// One SELL row held by one thread: the first kPre entries live in registers (loaded
-// before the PDL wait), the rest (rows longer than kPre) are streamed afterwards.
-struct RowHead {
-  int base, w, lane;
-  int c[kPre];
-  double v[kPre];
+// ---- TMA bulk staging of a CTA's matrix chunk ------------------------------------
+// A CTA owns kSlices consecutive SELL-32 slices; their column indices and values are
+// two contiguous ranges of the SELL arrays, so one elected thread brings each range
+// into shared memory with a single cp.async.bulk (TMA, SASS: UBLKCP) that completes on
+// an mbarrier.  The matrix is immutable during a solve, so the copy is issued BEFORE
+// the PDL wait and overlaps the tail of the previous kernel; it carries an L2
+// evict-first policy so the streamed matrix does not push the vectors out of L2.
+constexpr int kSlices = kBlock / 32;
+constexpr int kStageCapBytes = 46 * 1024;  // dynamic smem per CTA we are willing to use
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SMG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SMG_DONE;\n"
+      "bra SMG_WAIT;\n"
+      "SMG_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// Per-thread view of its row: first column / value entry (stride 32), width.
+struct RowView {
+  const int* cp;
+  const double* vp;
+  int w;
 };
 
-__device__ __forceinline__ void row_head_load(RowHead& h, int row, const int* __restrict__ slice_ptr,
+// Common prologue.  STAGED: issue the bulk copies of slices [slice0, slice0+kSlices),
+// return pointers into shared memory; otherwise pointers into the global SELL arrays.
+// Must be called by every thread of the CTA (contains __syncthreads); the caller waits
+// with stage_wait() after its PDL wait.
+template <bool STAGED>
+__device__ __forceinline__ RowView stage_rows(int slice0, int nslices, int row, bool active,
+                                              const int* __restrict__ slice_ptr,
                                               const int* __restrict__ col,
-                                              const double* __restrict__ val) {
-  const int s = row >> 5;
-  h.lane = row & 31;
-  h.base = slice_ptr[s];
-  h.w = (slice_ptr[s + 1] - h.base) >> 5;
-  const int* cp = col + h.base + h.lane;
-  const double* vp = val + h.base + h.lane;
-#pragma unroll
-  for (int t = 0; t < kPre; t++)
-    if (t < h.w) {
-      h.c[t] = ld_stream_s32(cp + t * 32);
-      h.v[t] = ld_stream_f64(vp + t * 32);
+                                              const double* __restrict__ val, int max_chunk,
+                                              unsigned char* dyn, uint64_t* bar) {
+  RowView rv;
+  rv.w = 0;
+  rv.cp = col;
+  rv.vp = val;
+  int base = 0;
+  if (active) {
+    const int s = row >> 5;
+    base = slice_ptr[s];
+    rv.w = (slice_ptr[s + 1] - base) >> 5;
+  }
+  if (STAGED) {
+    double* sval = reinterpret_cast<double*>(dyn);
+    int* scol = reinterpret_cast<int*>(dyn + (size_t)max_chunk * sizeof(double));
+    const int e0 = slice_ptr[slice0];
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      const int s1 = slice0 + kSlices < nslices ? slice0 + kSlices : nslices;
+      const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - e0);
+      const uint64_t pol = l2_evict_first_policy();
+      mbar_expect_tx(bar, nent * 12u);
+      if (nent > 0) {
+        bulk_g2s(sval, val + e0, nent * 8u, bar, pol);
+        bulk_g2s(scol, col + e0, nent * 4u, bar, pol);
+      }
     }
+    __syncthreads();  // the initialised barrier is visible to every waiter
+    rv.cp = scol + (base - e0) + (row & 31);
+    rv.vp = sval + (base - e0) + (row & 31);
+  } else {
+    rv.cp = col + base + (row & 31);
+    rv.vp = val + base + (row & 31);
+  }
+  return rv;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void stage_wait(uint64_t* bar) {
+  if (STAGED) mbar_wait(bar, 0);
 }
 
 // sum[q] += sum over the row's stored entries of val * x[col + q*ldx], entries in
-// storage order (ascending original index), products and sums rounded separately
-// (no FMA: the reference build has none).
-template <int K, bool SKIP_DIAG>
-__device__ __forceinline__ void row_accumulate(const RowHead& h, int row, const int* __restrict__ col,
-                                               const double* __restrict__ val, const double* x,
-                                               int ldx, double (&sum)[K]) {
-  double xv[kPre][K];
+// storage order, products and sums rounded separately (no FMA: the reference build has
+// none).  Gathers of a batch of kPre entries are issued together.
+template <int K, bool SKIP_DIAG, bool STAGED>
+__device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const double* x, int ldx,
+                                               double (&sum)[K]) {
+  for (int j0 = 0; j0 < rv.w; j0 += kPre) {
+    int c[kPre];
+    double xv[kPre][K];
 #pragma unroll
-  for (int t = 0; t < kPre; t++)
-    if (t < h.w && !(SKIP_DIAG && h.c[t] == row)) {
+    for (int t = 0; t < kPre; t++)
+      if (j0 + t < rv.w) {
+        c[t] = STAGED ? rv.cp[(j0 + t) * 32] : ld_stream_s32(rv.cp + (j0 + t) * 32);
+        if (!(SKIP_DIAG && c[t] == row)) {
 #pragma unroll
-      for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + h.c[t] + (size_t)q * ldx);
-    }
+#ifdef SMG_DEBUG_NOGATHER  // timing experiment only: perfectly coalesced "gathers"
+          for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + row + (c[t] & 1) + (size_t)q * ldx);
+#else
+          for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + c[t] + (size_t)q * ldx);
+#endif
+        }
+      }
 #pragma unroll
-  for (int t = 0; t < kPre; t++)
-    if (t < h.w && !(SKIP_DIAG && h.c[t] == row)) {
+    for (int t = 0; t < kPre; t++)
+      if (j0 + t < rv.w && !(SKIP_DIAG && c[t] == row)) {
+        const double v = STAGED ? rv.vp[(j0 + t) * 32] : ld_stream_f64(rv.vp + (j0 + t) * 32);
 #pragma unroll
-      for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(h.v[t], xv[t][q]));
-    }
-  const int* cp = col + h.base + h.lane;
-  const double* vp = val + h.base + h.lane;
-  for (int j = kPre; j < h.w; j++) {
-    const int c = ld_stream_s32(cp + j * 32);
-    const double v = ld_stream_f64(vp + j * 32);
-    if (SKIP_DIAG && c == row) continue;
-#pragma unroll
-    for (int q = 0; q < K; q++)
-      sum[q] = __dadd_rn(sum[q], __dmul_rn(v, ld_vec(x + c + (size_t)q * ldx)));
+        for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, xv[t][q]));
+      }
   }
 }
 
 enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3 };
 
 // y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
-template <int K, int MODE>
+template <int K, int MODE, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_apply_kernel(int nrows, const int* __restrict__ slice_ptr, const int* __restrict__ col,
-                  const double* __restrict__ val, const double* x, int ldx, const double* b,
-                  double* y, int ldy, double* z) {
+sell_apply_kernel(int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+                  const int* __restrict__ col, const double* __restrict__ val, const double* x,
+                  int ldx, const double* b, double* y, int ldy, double* z) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
   pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
   const bool active = row < nrows;
-  RowHead h;
-  h.w = 0;
-  if (active) row_head_load(h, row, slice_ptr, col, val);
+  const RowView rv = stage_rows<STAGED>(blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
+                                        val, max_chunk, dyn, &bar);
   pdl_wait();
+  stage_wait<STAGED>(&bar);
   if (!active) return;
   double sum[K];
 #pragma unroll
   for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, false>(h, row, col, val, x, ldx, sum);
+  row_accumulate<K, false, STAGED>(rv, row, x, ldx, sum);
 #pragma unroll
   for (int q = 0; q < K; q++) {
     const size_t o = row + (size_t)q * ldy;
@@ -157,24 +242,26 @@ sell_apply_kernel(int nrows, const int* __restrict__ slice_ptr, const int* __res
   }
 }
 
-template <int K>
+template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_residual_norm_kernel(int nrows, const int* __restrict__ slice_ptr,
+sell_residual_norm_kernel(int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                           const int* __restrict__ col, const double* __restrict__ val,
                           const double* x, const double* b, int ld, double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
   pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
   const bool active = row < nrows;
-  RowHead h;
-  h.w = 0;
-  if (active) row_head_load(h, row, slice_ptr, col, val);
+  const RowView rv = stage_rows<STAGED>(blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
+                                        val, max_chunk, dyn, &bar);
   pdl_wait();
+  stage_wait<STAGED>(&bar);
   double d2 = 0.0;
   if (active) {
     double sum[K];
 #pragma unroll
     for (int q = 0; q < K; q++) sum[q] = 0.0;
-    row_accumulate<K, false>(h, row, col, val, x, ld, sum);
+    row_accumulate<K, false, STAGED>(rv, row, x, ld, sum);
 #pragma unroll
     for (int q = 0; q < K; q++) {
       const double d = __dsub_rn(ld_vec(b + row + (size_t)q * ld), sum[q]);
@@ -214,27 +301,27 @@ reduce_partials_kernel(const double* partial, int n, double* __restrict__ out) {
 // One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
 // independent, so updating them in place and in parallel is exactly the sequential
 // sweep of mg_VCycle.cpp:147-158 restricted to those rows.
-template <int K>
+template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_gs_phase_kernel(int row0, int ps, int pe, const int* __restrict__ slice_ptr,
-                     const int* __restrict__ col, const double* __restrict__ val,
-                     const double* __restrict__ diag, const double* b, double* u, int ld) {
+sell_gs_phase_kernel(int row0, int ps, int pe, int nslices, int max_chunk,
+                     const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                     const double* __restrict__ val, const double* __restrict__ diag,
+                     const double* b, double* u, int ld) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
   pdl_launch_dependents();
   const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
   const bool active = row >= ps && row < pe;
-  RowHead h;
-  h.w = 0;
-  double d = 1.0;
-  if (active) {
-    row_head_load(h, row, slice_ptr, col, val);
-    d = ld_stream_f64(diag + row);
-  }
+  const RowView rv = stage_rows<STAGED>((row0 >> 5) + blockIdx.x * kSlices, nslices, row, active,
+                                        slice_ptr, col, val, max_chunk, dyn, &bar);
+  const double d = active ? ld_stream_f64(diag + row) : 1.0;
   pdl_wait();
+  stage_wait<STAGED>(&bar);
   if (!active) return;
   double sum[K];
 #pragma unroll
   for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, true>(h, row, col, val, u, ld, sum);
+  row_accumulate<K, true, STAGED>(rv, row, u, ld, sum);
 #pragma unroll
   for (int q = 0; q < K; q++) {
     const size_t o = row + (size_t)q * ld;
@@ -247,6 +334,7 @@ inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / blo
 }  // namespace
 
 void set_pdl_enabled(bool on) { g_use_pdl = on; }
+void set_tma_enabled(bool on) { g_use_tma = on; }
 
 #define SMG_DISPATCH_K(k, ...)                 \
   switch (k) {                                 \
@@ -256,37 +344,47 @@ void set_pdl_enabled(bool on) { g_use_pdl = on; }
     default: { constexpr int K = 4; __VA_ARGS__; } break; \
   }
 
+namespace {
+inline size_t stage_bytes(const SellDev& M) { return static_cast<size_t>(M.max_chunk) * 12; }
+inline bool use_staged(const SellDev& M) {
+  return g_use_tma && M.max_chunk > 0 && stage_bytes(M) <= static_cast<size_t>(kStageCapBytes);
+}
+
+template <int MODE>
+void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, const double* b,
+                  double* y, int ldy, double* z, int k, cudaStream_t st) {
+  if (M.nrows <= 0) return;
+  const int g = blocks_for(M.nrows, kBlock);
+  if (use_staged(M)) {
+    SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE, true>, g, kBlock, stage_bytes(M), st,
+                                    M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx,
+                                    b, y, ldy, z));
+  } else {
+    SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE, false>, g, kBlock, 0, st, M.nrows,
+                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx, b, y,
+                                    ldy, z));
+  }
+}
+}  // namespace
+
 void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
                  int k, cudaStream_t st) {
-  if (M.nrows <= 0) return;
-  const double* v = use_valT ? M.valT : M.val;
-  const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_SPMV>, g, kBlock, st, M.nrows,
-                                  M.slice_ptr, M.col, v, x, ldx, nullptr, y, ldy, nullptr));
+  launch_apply<MODE_SPMV>(M, use_valT ? M.valT : M.val, x, ldx, nullptr, y, ldy, nullptr, k, st);
 }
 
 void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, double* z, int ldy,
                       int k, cudaStream_t st) {
-  if (M.nrows <= 0) return;
-  const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_SPMV_ZERO>, g, kBlock, st, M.nrows,
-                                  M.slice_ptr, M.col, M.val, x, ldx, nullptr, y, ldy, z));
+  launch_apply<MODE_SPMV_ZERO>(M, M.val, x, ldx, nullptr, y, ldy, z, k, st);
 }
 
 void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
                      cudaStream_t st) {
-  if (M.nrows <= 0) return;
-  const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_RESIDUAL>, g, kBlock, st, M.nrows,
-                                  M.slice_ptr, M.col, M.valT, x, ld, b, r, ld, nullptr));
+  launch_apply<MODE_RESIDUAL>(M, M.valT, x, ld, b, r, ld, nullptr, k, st);
 }
 
 void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, int ldu, int k,
                         cudaStream_t st) {
-  if (M.nrows <= 0) return;
-  const int g = blocks_for(M.nrows, kBlock);
-  SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE_ADD>, g, kBlock, st, M.nrows,
-                                  M.slice_ptr, M.col, M.val, x, ldx, nullptr, u, ldu, nullptr));
+  launch_apply<MODE_ADD>(M, M.val, x, ldx, nullptr, u, ldu, nullptr, k, st);
 }
 
 int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, kBlock); }
@@ -294,9 +392,16 @@ int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, k
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st) {
   const int g = residual_norm_blocks(M.nrows);
-  SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K>, g, kBlock, st, M.nrows,
-                                  M.slice_ptr, M.col, M.valT, x, b, ld, scratch));
-  launch_kernel(reduce_partials_kernel, 1, 1024, st, scratch, g, out);
+  if (use_staged(M)) {
+    SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
+                                    st, M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
+                                    x, b, ld, scratch));
+  } else {
+    SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, M.nrows,
+                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT, x, b, ld,
+                                    scratch));
+  }
+  launch_kernel(reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
@@ -304,8 +409,15 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
   if (pe <= ps) return;
   const int row0 = ps & ~31;
   const int g = blocks_for(pe - row0, kBlock);
-  SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K>, g, kBlock, st, row0, ps, pe,
-                                  M.slice_ptr, M.col, M.val, diag, b, u, ld));
+  if (use_staged(M)) {
+    SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K, true>, g, kBlock, stage_bytes(M), st,
+                                    row0, ps, pe, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val,
+                                    diag, b, u, ld));
+  } else {
+    SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K, false>, g, kBlock, 0, st, row0, ps, pe,
+                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val, diag, b, u,
+                                    ld));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -573,7 +685,7 @@ void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n
                            cudaStream_t st) {
   if (n <= 0) return;
   const int g = blocks_for(n, kBlock / 32);
-  SMG_DISPATCH_K(k, launch_kernel(dense_symv_add_kernel<K>, g, kBlock, st, Ainv, b, u, n));
+  SMG_DISPATCH_K(k, launch_kernel(dense_symv_add_kernel<K>, g, kBlock, 0, st, Ainv, b, u, n));
 }
 void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
                           int n_known, const int* g, const int* auk_ptr, const int* auk_q,
@@ -602,7 +714,7 @@ void launch_permute_out(const double* in, const int* perm, double* out, int n, i
   if (n > 0) permute_out_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
 }
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
-  if (n > 0) launch_kernel(fill_kernel, blocks_for(n, 256), 256, st, p, v, n);
+  if (n > 0) launch_kernel(fill_kernel, blocks_for(n, 256), 256, 0, st, p, v, n);
 }
 
 }  // namespace smg

@@ -13,6 +13,7 @@ namespace smg {
 struct SellDev {
   int nrows = 0;
   int nslices = 0;
+  int max_chunk = 0;  // most stored entries in any 8 consecutive slices (one CTA's chunk)
   const int* slice_ptr = nullptr;
   const int* col = nullptr;
   const double* val = nullptr;
@@ -29,6 +30,8 @@ void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, dou
                       int k, cudaStream_t st);
 // programmatic dependent launch of the hot-path kernels (default on)
 void set_pdl_enabled(bool on);
+// TMA (cp.async.bulk) staging of the matrix chunks in shared memory (default on)
+void set_tma_enabled(bool on);
 // r = b - M x
 void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
                      cudaStream_t st);

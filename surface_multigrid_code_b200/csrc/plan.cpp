@@ -277,7 +277,7 @@ RowOrder make_row_order(const Csc& A, const std::vector<int>& phase, int n_phase
 }
 
 Sell build_sell(const Csc& X, const std::vector<int>& row_perm,
-                const std::vector<int>& col_iperm) {
+                const std::vector<int>& col_iperm, bool sort_cols) {
   Sell S;
   const int n = X.cols;
   S.nrows = n;
@@ -300,6 +300,7 @@ Sell build_sell(const Csc& X, const std::vector<int>& row_perm,
   const int64_t tot = S.slice_ptr[S.nslices];
   S.col.assign(tot, 0);
   S.src.assign(tot, -1);
+  std::vector<std::pair<int, int>> ent;
   for (int s = 0; s < S.nslices; s++) {
     const int base = S.slice_ptr[s];
     const int w = (S.slice_ptr[s + 1] - base) / kSliceRows;
@@ -309,10 +310,14 @@ Sell build_sell(const Csc& X, const std::vector<int>& row_perm,
       int last_col = (r < n) ? 0 : 0;
       if (r < n) {
         const int c = row_perm[r];
-        for (int p = X.colptr[c]; p < X.colptr[c + 1]; p++, j++) {
-          last_col = col_iperm[X.rowidx[p]];
-          S.col[base + j * kSliceRows + lane] = last_col;
-          S.src[base + j * kSliceRows + lane] = p;
+        ent.clear();
+        for (int p = X.colptr[c]; p < X.colptr[c + 1]; p++) ent.emplace_back(col_iperm[X.rowidx[p]], p);
+        if (sort_cols) std::sort(ent.begin(), ent.end());
+        for (const auto& e : ent) {
+          last_col = e.first;
+          S.col[base + j * kSliceRows + lane] = e.first;
+          S.src[base + j * kSliceRows + lane] = e.second;
+          j++;
         }
       }
       // padding: zero value, column = last real column of the row (same sector)
@@ -385,7 +390,7 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
   }
   if (n == 0) L.n_phases = 0;
   L.order = make_row_order(A, L.phase, L.n_phases, rank, opt.sigma);
-  L.sellA = build_sell(A, L.order.perm, L.order.iperm);
+  L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
   remap_src(L.sellA, L.live_src);
 }
 
@@ -396,7 +401,9 @@ static bool pattern_symmetric(const Csc& A, std::vector<int>* tmap) {
 }
 
 int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc>& P_full,
-               const PlanOptions& opt, Plan* plan) {
+               const PlanOptions& opt_in, Plan* plan) {
+  PlanOptions opt = opt_in;
+  if (opt.sort_cols < 0) opt.sort_cols = opt.smoother == SMG_SMOOTHER_MULTICOLOUR ? 1 : 0;
   Plan& pl = *plan;
   pl = Plan();
   const int nlev = static_cast<int>(P_full.size()) + 1;
@@ -519,10 +526,10 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
   for (int l = 1; l < nlev; l++) {
     LevelPlan& L = pl.lv[l];
     // y_fine = P x_coarse : rows of P = columns of PT's CSC (explicit zeros skipped)
-    L.sellP = build_sell(PTz[l], pl.lv[l - 1].order.perm, L.order.iperm);
+    L.sellP = build_sell(PTz[l], pl.lv[l - 1].order.perm, L.order.iperm, opt.sort_cols > 0);
     remap_src(L.sellP, ptz_src[l]);
     // y_coarse = PT x_fine : rows of PT = columns of P's CSC
-    L.sellPT = build_sell(Pz[l], L.order.perm, pl.lv[l - 1].order.iperm);
+    L.sellPT = build_sell(Pz[l], L.order.perm, pl.lv[l - 1].order.iperm, opt.sort_cols > 0);
     remap_src(L.sellPT, pz_src[l]);
     if (L.sellP.nrows < 0 || L.sellPT.nrows < 0) {
       pl.error = "transfer operator too large for 32-bit SELL offsets";

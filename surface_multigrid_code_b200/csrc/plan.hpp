@@ -65,7 +65,11 @@ struct Sell {
 // PT into the row-wise storage of PT / P).  Row r of the result is X column
 // row_perm[r]; entry order inside a row = CSC order (ascending original index, the
 // reference's accumulation order); stored column index = col_iperm[X.rowidx].
-Sell build_sell(const Csc& X, const std::vector<int>& row_perm, const std::vector<int>& col_iperm);
+// sort_cols: order the entries of a row by stored (permuted) column instead, which
+// makes the gathers of neighbouring lanes fall into the same sectors (fast mode only:
+// it changes the floating-point summation order).
+Sell build_sell(const Csc& X, const std::vector<int>& row_perm, const std::vector<int>& col_iperm,
+                bool sort_cols = false);
 
 struct RowOrder {
   std::vector<int> perm;       // new -> old
@@ -109,6 +113,7 @@ struct PlanOptions {
   int smoother = 1;  // 0 wavefront, 1 multicolour
   int locality_reorder = 1;
   int sigma = 256;
+  int sort_cols = -1;  // -1: on for multicolour, off for wavefront (bit-parity order)
 };
 
 struct Plan {

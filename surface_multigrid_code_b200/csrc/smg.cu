@@ -89,12 +89,13 @@ struct DevBuf {
 struct SellBufs {
   DevBuf<int> slice_ptr, col, src;
   DevBuf<double> val, valT;
-  int nrows = 0, nslices = 0;
+  int nrows = 0, nslices = 0, max_chunk = 0;
   int64_t padded = 0;
   SellDev view() const {
     SellDev d;
     d.nrows = nrows;
     d.nslices = nslices;
+    d.max_chunk = max_chunk;
     d.slice_ptr = slice_ptr.p;
     d.col = col.p;
     d.val = val.p;
@@ -206,6 +207,11 @@ int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT
   out->nrows = S.nrows;
   out->nslices = S.nslices;
   out->padded = S.padded();
+  out->max_chunk = 0;
+  for (int s0 = 0; s0 < S.nslices; s0++) {  // any 8 consecutive slices: one CTA's TMA chunk
+    const int s1 = std::min(S.nslices, s0 + 8);
+    out->max_chunk = std::max(out->max_chunk, S.slice_ptr[s1] - S.slice_ptr[s0]);
+  }
   SMG_CUDA(h, out->slice_ptr.upload(S.slice_ptr, h->stream));
   SMG_CUDA(h, out->col.upload(S.col, h->stream));
   SMG_CUDA(h, out->src.upload(S.src, h->stream));
@@ -753,6 +759,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   }
   h->device = dev;
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
+  if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 64 * sizeof(double)) != cudaSuccess) {
     smg_destroy(h);

@@ -55,26 +55,34 @@ def test_galerkin_and_diag_bit_exact(problems, name):
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("smoother", ["wavefront", "multicolour"])
 def test_linear_operators_bit_exact(problems, name, smoother):
-    """A, residual, restrict, prolong do not depend on the smoother schedule (only the
-    row numbering does): bit-exact in both modes."""
+    """A, residual, restrict, prolong: bit-exact in wavefront (parity) mode, where rows
+    keep the reference's ascending-index accumulation order; in multicolour (fast) mode
+    the entries of a row are stored sorted by permuted column (gather locality), so the
+    sums are reordered: equal to a few ulps of the row's magnitude."""
     pr = problems[name]
     ora, s = _pair(pr, smoother)
     rng = np.random.default_rng(11)
     k = pr.k
+
+    def same(a, b):
+        if smoother == "wavefront":
+            return np.array_equal(a, b)
+        return np.allclose(a, b, rtol=0, atol=1e-13 * max(1.0, float(np.abs(b).max())))
+
     for lv in range(pr.nlev):
         n = s.level_rows(lv)
         assert n == ora.level_rows(lv)
         u, b = _rand(rng, n, k), _rand(rng, n, k)
         au = s.apply_A(lv, u)
-        assert np.array_equal(au, ora.apply_A(lv, u))
-        assert np.array_equal(s.residual(lv, b, u), b - ora.apply_A(lv, u))
+        assert same(au, ora.apply_A(lv, u))
+        assert same(s.residual(lv, b, u), b - ora.apply_A(lv, u))
         ref = np.linalg.norm(b - ora.apply_A(lv, u))
         assert abs(s.residual_norm(lv, b, u) - ref) <= 1e-12 * ref
         if lv + 1 < pr.nlev:
             nc = s.level_rows(lv + 1)
-            assert np.array_equal(s.restrict(lv, u), ora.restrict(lv, u))
+            assert same(s.restrict(lv, u), ora.restrict(lv, u))
             uc = _rand(rng, nc, k)
-            assert np.array_equal(s.prolong(lv, uc), ora.prolong(lv, uc))
+            assert same(s.prolong(lv, uc), ora.prolong(lv, uc))
     s.close()
 
 
