@@ -198,6 +198,12 @@ typedef enum smg_kernel_id {
 } smg_kernel_id;
 int smg_time_kernel(smg_handle *h, int which, int lv, int k, int reps, int flush_l2,
                     float *ms_per_rep, int *launches_per_rep);
+/* Device timeline of one solve-loop iteration (residual norm + V-cycle, replayed as a
+ * CUDA graph with PDL edges): for every kernel launch the earliest CTA start and the
+ * latest CTA end (%globaltimer), in microseconds from the first start.  `names`
+ * receives one '\n'-terminated label per event.  Profiling aid, not on the hot path. */
+int smg_trace_iteration(smg_handle *h, int k, int max_events, char *names, int names_cap,
+                        double *t0_us, double *t1_us, int *n_events);
 /* kernel launches issued by this handle since creation (your-kernels only;
  * graph replays count their kernel nodes) */
 int64_t smg_launch_count(const smg_handle *h);

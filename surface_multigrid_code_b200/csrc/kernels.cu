@@ -14,6 +14,9 @@
 // parity in wavefront mode depends on it.
 #include "kernels.hpp"
 
+#include <string>
+#include <vector>
+
 namespace smg {
 
 namespace {
@@ -53,9 +56,35 @@ __device__ __forceinline__ double ld_vec(const double* p) {  // mutable vector d
 bool g_use_pdl = true;
 bool g_use_tma = true;
 
+// ---- optional in-kernel timeline (smg_trace_*): every CTA folds %globaltimer at its
+// start / end into [min start, max end] of the launch's slot.  slot < 0: off.
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(int slot) {
+  if (slot >= 0 && threadIdx.x == 0) atomicMin(g_trace_buf + 2 * slot, global_timer());
+}
+__device__ __forceinline__ void trace_end(int slot) {
+  if (slot >= 0 && threadIdx.x == 0) atomicMax(g_trace_buf + 2 * slot + 1, global_timer());
+}
+struct TraceState {
+  bool on = false;
+  int next = 0, cap = 0;
+  std::string label;
+  std::vector<std::string> names;
+} g_trace;
+
 template <class... KArgs, class... Args>
-void launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
-                   Args... args) {
+void launch_kernel(const char* name, void (*kernel)(int, KArgs...), int grid, int block, size_t smem,
+                   cudaStream_t st, Args... args) {
+  int slot = -1;
+  if (g_trace.on && g_trace.next < g_trace.cap) {
+    slot = g_trace.next++;
+    g_trace.names.push_back(g_trace.label + " " + name + " g" + std::to_string(grid));
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -66,7 +95,7 @@ void launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  cudaLaunchKernelEx(&cfg, kernel, slot, static_cast<KArgs>(args)...);
 }
 
 // ---- TMA bulk staging of a CTA's matrix chunk ------------------------------------
@@ -191,7 +220,7 @@ __device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const
         if (!(SKIP_DIAG && c[t] == row)) {
 #pragma unroll
 #ifdef SMG_DEBUG_NOGATHER  // timing experiment only: perfectly coalesced "gathers"
-          for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + row + (c[t] & 1) + (size_t)q * ldx);
+          for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + (row < ldx - 2 ? row : ldx - 2) + (c[t] & 1) + (size_t)q * ldx);
 #else
           for (int q = 0; q < K; q++) xv[t][q] = ld_vec(x + c[t] + (size_t)q * ldx);
 #endif
@@ -212,11 +241,12 @@ enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3 };
 // y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
 template <int K, int MODE, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_apply_kernel(int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+sell_apply_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                   const int* __restrict__ col, const double* __restrict__ val, const double* x,
                   int ldx, const double* b, double* y, int ldy, double* z) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
   const bool active = row < nrows;
@@ -224,31 +254,34 @@ sell_apply_kernel(int nrows, int nslices, int max_chunk, const int* __restrict__
                                         val, max_chunk, dyn, &bar);
   pdl_wait();
   stage_wait<STAGED>(&bar);
-  if (!active) return;
-  double sum[K];
+  if (active) {
+    double sum[K];
 #pragma unroll
-  for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, false, STAGED>(rv, row, x, ldx, sum);
+    for (int q = 0; q < K; q++) sum[q] = 0.0;
+    row_accumulate<K, false, STAGED>(rv, row, x, ldx, sum);
 #pragma unroll
-  for (int q = 0; q < K; q++) {
-    const size_t o = row + (size_t)q * ldy;
-    if (MODE == MODE_SPMV) y[o] = sum[q];
-    if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(ld_vec(b + o), sum[q]);
-    if (MODE == MODE_ADD) y[o] = __dadd_rn(ld_vec(y + o), sum[q]);
-    if (MODE == MODE_SPMV_ZERO) {
-      y[o] = sum[q];
-      z[o] = 0.0;
+    for (int q = 0; q < K; q++) {
+      const size_t o = row + (size_t)q * ldy;
+      if (MODE == MODE_SPMV) y[o] = sum[q];
+      if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(ld_vec(b + o), sum[q]);
+      if (MODE == MODE_ADD) y[o] = __dadd_rn(ld_vec(y + o), sum[q]);
+      if (MODE == MODE_SPMV_ZERO) {
+        y[o] = sum[q];
+        z[o] = 0.0;
+      }
     }
   }
+  trace_end(trace_slot);
 }
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_residual_norm_kernel(int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+sell_residual_norm_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                           const int* __restrict__ col, const double* __restrict__ val,
                           const double* x, const double* b, int ld, double* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   const int row = blockIdx.x * kBlock + threadIdx.x;
   const bool active = row < nrows;
@@ -280,10 +313,12 @@ sell_residual_norm_kernel(int nrows, int nslices, int max_chunk, const int* __re
     for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
     partial[blockIdx.x] = t;
   }
+  trace_end(trace_slot);
 }
 
 __global__ void __launch_bounds__(1024)
-reduce_partials_kernel(const double* partial, int n, double* __restrict__ out) {
+reduce_partials_kernel(int trace_slot, const double* partial, int n, double* __restrict__ out) {
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double sm[1024];
@@ -296,6 +331,7 @@ reduce_partials_kernel(const double* partial, int n, double* __restrict__ out) {
     __syncthreads();
   }
   if (threadIdx.x == 0) *out = sm[0];
+  trace_end(trace_slot);
 }
 
 // One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
@@ -303,12 +339,13 @@ reduce_partials_kernel(const double* partial, int n, double* __restrict__ out) {
 // sweep of mg_VCycle.cpp:147-158 restricted to those rows.
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_gs_phase_kernel(int row0, int ps, int pe, int nslices, int max_chunk,
+sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int max_chunk,
                      const int* __restrict__ slice_ptr, const int* __restrict__ col,
                      const double* __restrict__ val, const double* __restrict__ diag,
                      const double* b, double* u, int ld) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
   const bool active = row >= ps && row < pe;
@@ -317,16 +354,18 @@ sell_gs_phase_kernel(int row0, int ps, int pe, int nslices, int max_chunk,
   const double d = active ? ld_stream_f64(diag + row) : 1.0;
   pdl_wait();
   stage_wait<STAGED>(&bar);
-  if (!active) return;
-  double sum[K];
+  if (active) {
+    double sum[K];
 #pragma unroll
-  for (int q = 0; q < K; q++) sum[q] = 0.0;
-  row_accumulate<K, true, STAGED>(rv, row, u, ld, sum);
+    for (int q = 0; q < K; q++) sum[q] = 0.0;
+    row_accumulate<K, true, STAGED>(rv, row, u, ld, sum);
 #pragma unroll
-  for (int q = 0; q < K; q++) {
-    const size_t o = row + (size_t)q * ld;
-    u[o] = __ddiv_rn(__dsub_rn(ld_vec(b + o), sum[q]), d);
+    for (int q = 0; q < K; q++) {
+      const size_t o = row + (size_t)q * ld;
+      u[o] = __ddiv_rn(__dsub_rn(ld_vec(b + o), sum[q]), d);
+    }
   }
+  trace_end(trace_slot);
 }
 
 inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
@@ -334,6 +373,17 @@ inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / blo
 }  // namespace
 
 void set_pdl_enabled(bool on) { g_use_pdl = on; }
+void trace_start(unsigned long long* dev_buf, int cap) {
+  cudaMemcpyToSymbol(g_trace_buf, &dev_buf, sizeof(dev_buf));
+  g_trace.on = true;
+  g_trace.next = 0;
+  g_trace.cap = cap;
+  g_trace.names.clear();
+}
+void trace_stop() { g_trace.on = false; }
+void trace_label(const char* label) { g_trace.label = label; }
+int trace_count() { return g_trace.next; }
+const char* trace_name(int i) { return g_trace.names[i].c_str(); }
 void set_tma_enabled(bool on) { g_use_tma = on; }
 
 #define SMG_DISPATCH_K(k, ...)                 \
@@ -345,6 +395,7 @@ void set_tma_enabled(bool on) { g_use_tma = on; }
   }
 
 namespace {
+const char* const kApplyNames[4] = {"spmv", "residual", "prolong_add", "restrict_zero"};
 inline size_t stage_bytes(const SellDev& M) { return static_cast<size_t>(M.max_chunk) * 12; }
 inline bool use_staged(const SellDev& M) {
   return g_use_tma && M.max_chunk > 0 && stage_bytes(M) <= static_cast<size_t>(kStageCapBytes);
@@ -356,11 +407,11 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
   if (M.nrows <= 0) return;
   const int g = blocks_for(M.nrows, kBlock);
   if (use_staged(M)) {
-    SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE, true>, g, kBlock, stage_bytes(M), st,
+    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, true>, g, kBlock, stage_bytes(M), st,
                                     M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx,
                                     b, y, ldy, z));
   } else {
-    SMG_DISPATCH_K(k, launch_kernel(sell_apply_kernel<K, MODE, false>, g, kBlock, 0, st, M.nrows,
+    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, false>, g, kBlock, 0, st, M.nrows,
                                     M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx, b, y,
                                     ldy, z));
   }
@@ -393,15 +444,15 @@ void launch_residual_norm2(const SellDev& M, const double* b, const double* x, i
                            double* scratch, double* out, cudaStream_t st) {
   const int g = residual_norm_blocks(M.nrows);
   if (use_staged(M)) {
-    SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
+    SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
                                     st, M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
                                     x, b, ld, scratch));
   } else {
-    SMG_DISPATCH_K(k, launch_kernel(sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, M.nrows,
+    SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, M.nrows,
                                     M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT, x, b, ld,
                                     scratch));
   }
-  launch_kernel(reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
+  launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
@@ -410,11 +461,11 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
   const int row0 = ps & ~31;
   const int g = blocks_for(pe - row0, kBlock);
   if (use_staged(M)) {
-    SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K, true>, g, kBlock, stage_bytes(M), st,
+    SMG_DISPATCH_K(k, launch_kernel("gs_phase", sell_gs_phase_kernel<K, true>, g, kBlock, stage_bytes(M), st,
                                     row0, ps, pe, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val,
                                     diag, b, u, ld));
   } else {
-    SMG_DISPATCH_K(k, launch_kernel(sell_gs_phase_kernel<K, false>, g, kBlock, 0, st, row0, ps, pe,
+    SMG_DISPATCH_K(k, launch_kernel("gs_phase", sell_gs_phase_kernel<K, false>, g, kBlock, 0, st, row0, ps, pe,
                                     M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val, diag, b, u,
                                     ld));
   }
@@ -535,7 +586,9 @@ __global__ void symmetrize_lower_kernel(double* D, int n) {
 // read as the contiguous column i.
 template <int K>
 __global__ void __launch_bounds__(kBlock)
-dense_symv_add_kernel(const double* __restrict__ Ainv, const double* b, double* u, int n) {
+dense_symv_add_kernel(int trace_slot, const double* __restrict__ Ainv, const double* b, double* u,
+                      int n) {
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   const int i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -550,7 +603,10 @@ dense_symv_add_kernel(const double* __restrict__ Ainv, const double* b, double* 
     ahead[t] = (i < n && j < n) ? ld_stream_f64(a + j) : 0.0;
   }
   pdl_wait();
-  if (i >= n) return;
+  if (i >= n) {
+    trace_end(trace_slot);
+    return;
+  }
   double acc[K];
 #pragma unroll
   for (int q = 0; q < K; q++) acc[q] = 0.0;
@@ -573,6 +629,102 @@ dense_symv_add_kernel(const double* __restrict__ Ainv, const double* b, double* 
     for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
     if (lane == 0) u[i + (size_t)q * n] = ld_vec(u + i + (size_t)q * n) + acc[q];
   }
+  trace_end(trace_slot);
+}
+
+// ---- coarse direct solve: u += Ainv * b with Ainv symmetric -----------------------
+// Only the lower-triangular 64x64 tiles of the dense inverse are read (half the
+// bytes): tile (I,J), I >= J, contributes  y_I += T b_J  and, for I != J,
+// y_J += T^T b_I.  Every contribution to block-row X is written to its own slot
+// (slot = index of the other block), and dense_sym_reduce_kernel sums the slots in a
+// fixed order: deterministic, no floating-point atomics.
+constexpr int kTile = 64;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+dense_sym_tile_kernel(int trace_slot, const double* __restrict__ Ainv, const double* b,
+                      double* __restrict__ partial, int n, int ldb) {
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  // triangular tile index -> (I, J), J <= I
+  const int t = blockIdx.x;
+  int I = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+  while ((I + 1) * (I + 2) / 2 <= t) I++;
+  while (I * (I + 1) / 2 > t) I--;
+  const int J = t - I * (I + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = I * kTile + lane, r1 = r0 + 32;
+  const int c0 = J * kTile + warp * 8;
+  double m0[8], m1[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {  // immutable during a solve: fetched before the PDL wait
+    const size_t col = static_cast<size_t>(c0 + c) * n;
+    m0[c] = (c0 + c < n && r0 < n) ? ld_stream_f64(Ainv + col + r0) : 0.0;
+    m1[c] = (c0 + c < n && r1 < n) ? ld_stream_f64(Ainv + col + r1) : 0.0;
+  }
+  pdl_wait();
+  __shared__ double red[8][kTile];
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const double* bq = b + static_cast<size_t>(q) * ldb;
+    // row part: y_I[r] += sum_c T[r][c] * b_J[c]
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const double bj = (c0 + c < n) ? ld_vec(bq + c0 + c) : 0.0;
+      a0 += m0[c] * bj;
+      a1 += m1[c] * bj;
+    }
+    red[warp][lane] = a0;
+    red[warp][lane + 32] = a1;
+    __syncthreads();
+    if (threadIdx.x < kTile) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) sum += red[w][threadIdx.x];
+      const int r = I * kTile + threadIdx.x;
+      if (r < n) partial[(static_cast<size_t>(J) * K + q) * n + r] = sum;
+    }
+    __syncthreads();
+    // column part: y_J[c] += sum_r T[r][c] * b_I[r]
+    if (I != J) {
+      const double bi0 = r0 < n ? ld_vec(bq + r0) : 0.0;
+      const double bi1 = r1 < n ? ld_vec(bq + r1) : 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        double v = m0[c] * bi0 + m1[c] * bi1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && c0 + c < n) partial[(static_cast<size_t>(I) * K + q) * n + c0 + c] = v;
+      }
+    }
+  }
+  trace_end(trace_slot);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+dense_sym_reduce_kernel(int trace_slot, const double* partial, double* u, int n, int nblk, int ldu) {
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) {
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      double sum = 0.0;
+      for (int s0 = 0; s0 < nblk; s0 += 16) {  // 16 independent loads in flight, summed in order
+        double v[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++)
+          v[t] = s0 + t < nblk ? ld_vec(partial + (static_cast<size_t>(s0 + t) * K + q) * n + i) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) sum += v[t];
+      }
+      u[i + static_cast<size_t>(q) * ldu] = ld_vec(u + i + static_cast<size_t>(q) * ldu) + sum;
+    }
+  }
+  trace_end(trace_slot);
 }
 
 __global__ void gather_system_kernel(const double* __restrict__ RHS,
@@ -633,7 +785,8 @@ __global__ void permute_out_kernel(const double* __restrict__ in, const int* __r
   for (int q = 0; q < k; q++) out[d + (size_t)q * n] = in[i + (size_t)q * n];
 }
 
-__global__ void fill_kernel(double* p, double v, int64_t n) {
+__global__ void fill_kernel(int trace_slot, double* p, double v, int64_t n) {
+  (void)trace_slot;
   pdl_launch_dependents();
   pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,11 +834,25 @@ void launch_symmetrize_lower(double* D, int n, cudaStream_t st) {
   dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8);
   symmetrize_lower_kernel<<<g, b, 0, st>>>(D, n);
 }
+size_t dense_sym_scratch_doubles(int n, int k) {
+  const int nblk = (n + kTile - 1) / kTile;
+  return static_cast<size_t>(nblk) * (k < kMaxK ? k : kMaxK) * n;
+}
+void launch_dense_sym_add(const double* Ainv, const double* b, double* u, double* scratch, int n,
+                          int k, cudaStream_t st) {
+  if (n <= 0) return;
+  const int nblk = (n + kTile - 1) / kTile;
+  const int ntiles = nblk * (nblk + 1) / 2;
+  SMG_DISPATCH_K(k, launch_kernel("coarse_tiles", dense_sym_tile_kernel<K>, ntiles, 256, 0, st, Ainv,
+                                  b, scratch, n, n));
+  SMG_DISPATCH_K(k, launch_kernel("coarse_reduce", dense_sym_reduce_kernel<K>, blocks_for(n, 256),
+                                  256, 0, st, scratch, u, n, nblk, n));
+}
 void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
                            cudaStream_t st) {
   if (n <= 0) return;
   const int g = blocks_for(n, kBlock / 32);
-  SMG_DISPATCH_K(k, launch_kernel(dense_symv_add_kernel<K>, g, kBlock, 0, st, Ainv, b, u, n));
+  SMG_DISPATCH_K(k, launch_kernel("coarse_symv", dense_symv_add_kernel<K>, g, kBlock, 0, st, Ainv, b, u, n));
 }
 void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
                           int n_known, const int* g, const int* auk_ptr, const int* auk_q,
@@ -714,7 +881,7 @@ void launch_permute_out(const double* in, const int* perm, double* out, int n, i
   if (n > 0) permute_out_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
 }
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
-  if (n > 0) launch_kernel(fill_kernel, blocks_for(n, 256), 256, 0, st, p, v, n);
+  if (n > 0) launch_kernel("fill", fill_kernel, blocks_for(n, 256), 256, 0, st, p, v, n);
 }
 
 }  // namespace smg

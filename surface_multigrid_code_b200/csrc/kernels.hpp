@@ -32,6 +32,13 @@ void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, dou
 void set_pdl_enabled(bool on);
 // TMA (cp.async.bulk) staging of the matrix chunks in shared memory (default on)
 void set_tma_enabled(bool on);
+// in-kernel timeline: slots of 2 x u64 [min start, max end] in nanoseconds (%globaltimer);
+// the caller initialises the buffer to {~0, 0} per slot
+void trace_start(unsigned long long* dev_buf, int cap);
+void trace_stop();
+void trace_label(const char* label);
+int trace_count();
+const char* trace_name(int i);
 // r = b - M x
 void launch_residual(const SellDev& M, const double* b, const double* x, double* r, int ld, int k,
                      cudaStream_t st);
@@ -74,7 +81,12 @@ void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const do
                          const int* iperm, double* D, int n, cudaStream_t st);
 // mirror the lower triangle of a column-major n x n matrix into the upper one
 void launch_symmetrize_lower(double* D, int n, cudaStream_t st);
-// u = u + Ainv * b  (Ainv symmetric dense n x n; b,u: n x k)
+// u = u + Ainv * b reading only the lower-triangular 64x64 tiles of the symmetric Ainv;
+// scratch must hold dense_sym_scratch_doubles(n, k) doubles
+size_t dense_sym_scratch_doubles(int n, int k);
+void launch_dense_sym_add(const double* Ainv, const double* b, double* u, double* scratch, int n,
+                          int k, cudaStream_t st);
+// u = u + Ainv * b  (Ainv symmetric dense n x n; b,u: n x k), one warp per full row
 void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
                            cudaStream_t st);
 

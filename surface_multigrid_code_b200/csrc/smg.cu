@@ -155,7 +155,7 @@ struct smg_handle {
   int n_known_distinct = 0;
 
   // coarse direct solve
-  DevBuf<double> ainv;
+  DevBuf<double> ainv, coarse_scratch;
   DevBuf<double> potrf_work;
   DevBuf<int> dev_info;
 
@@ -224,6 +224,7 @@ int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT
 int ensure_k(smg_handle* h, int k) {
   if (k <= h->kcap) return SMG_OK;
   drop_graphs(h);
+  SMG_CUDA(h, h->coarse_scratch.reserve(smg::dense_sym_scratch_doubles(h->lv.back().n, k)));
   for (auto& L : h->lv) {
     const size_t cnt = static_cast<size_t>(L.n) * k;
     SMG_CUDA(h, L.b.alloc(cnt));
@@ -308,8 +309,8 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L.n;
-    smg::launch_dense_symv_add(h->ainv.p, b + o, u + o, L.n, kk, h->stream);
-    h->launches++;
+    smg::launch_dense_sym_add(h->ainv.p, b + o, u + o, h->coarse_scratch.p, L.n, kk, h->stream);
+    h->launches += 2;
   }
 }
 
@@ -317,16 +318,23 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
 // work vectors lv[l].b / .u of levels l >= lv0.
 void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
   const int last = static_cast<int>(h->lv.size()) - 1;
+  char label[32];
   for (int l = lv0; l < last; l++) {
     LevelDev& L = h->lv[l];
     LevelDev& C = h->lv[l + 1];
+    std::snprintf(label, sizeof(label), "L%d down", l);
+    smg::trace_label(label);
     relax_device(h, l, pre, L.b.p, L.u.p, k);              // :36
     residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
     restrict_device(h, l, L.r.p, C.b.p, k, C.u.p);         // :44 and uc = 0 (:46-47), fused
   }
+  std::snprintf(label, sizeof(label), "L%d", last);
+  smg::trace_label(label);
   coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
   for (int l = last - 1; l >= lv0; l--) {
     LevelDev& L = h->lv[l];
+    std::snprintf(label, sizeof(label), "L%d up", l);
+    smg::trace_label(label);
     prolong_device(h, l, h->lv[l + 1].u.p, L.u.p, k, true);  // :52-53
     relax_device(h, l, post, L.b.p, L.u.p, k);               // :56
   }
@@ -787,7 +795,7 @@ void smg_destroy(smg_handle* h) {
     h->a_in.release(); h->lhs_src.release(); h->auk_src.release(); h->g.release();
     h->auk_ptr.release(); h->auk_q.release(); h->auk_pos.release();
     h->auk_csc_val.release(); h->auk_val.release(); h->kidx.release(); h->ksrc.release();
-    h->ainv.release(); h->potrf_work.release(); h->dev_info.release();
+    h->ainv.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
     h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1210,6 +1218,68 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
   SMG_TRY(check_launch(h, "time_kernel"));
   *ms_per_rep = static_cast<float>(total / reps);
   if (launches_per_rep) *launches_per_rep = static_cast<int>(per_rep);
+  return SMG_OK;
+}
+
+int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int names_cap,
+                        double* t0_us, double* t1_us, int* n_events) {
+  SMG_TRY(check_ready(h, true));
+  if (!names || !t0_us || !t1_us || !n_events || k < 1 || max_events < 1)
+    return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  SMG_TRY(ensure_k(h, k));
+  DevBuf<unsigned long long> buf;
+  SMG_CUDA(h, buf.alloc(static_cast<size_t>(max_events) * 2));
+  std::vector<unsigned long long> init(static_cast<size_t>(max_events) * 2);
+  for (int i = 0; i < max_events; i++) {
+    init[2 * i] = ~0ull;
+    init[2 * i + 1] = 0ull;
+  }
+  LevelDev& L0 = h->lv[0];
+  const int64_t launches_before = h->launches;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  // the traced graph is built with the trace slots baked in and never cached
+  SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
+  SMG_CUDA(h, h->norm_out.reserve(4));
+  smg::trace_start(buf.p, max_events);
+  smg::trace_label("norm");
+  cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    smg::launch_residual_norm2(L0.sellA.view(), L0.b.p, L0.u.p, L0.n, std::min(k, smg::kMaxK),
+                               h->norm_scratch.p, h->norm_out.p, h->stream);
+    vcycle_device(h, 0, h->opt.pre_relax, h->opt.post_relax, k);
+    e = cudaStreamEndCapture(h->stream, &graph);
+  }
+  smg::trace_stop();
+  h->launches = launches_before;
+  if (e != cudaSuccess) return fail(h, SMG_E_CUDA, std::string("trace capture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(h, SMG_E_CUDA, std::string("trace instantiate: ") + cudaGetErrorString(e));
+  for (int rep = 0; rep < 3; rep++) {  // the last replay is the one reported
+    cudaMemcpyAsync(buf.p, init.data(), init.size() * sizeof(unsigned long long),
+                    cudaMemcpyHostToDevice, h->stream);
+    cudaGraphLaunch(exec, h->stream);
+  }
+  std::vector<unsigned long long> out(init.size());
+  cudaMemcpyAsync(out.data(), buf.p, out.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                  h->stream);
+  e = cudaStreamSynchronize(h->stream);
+  cudaGraphExecDestroy(exec);
+  if (e != cudaSuccess) return fail(h, SMG_E_CUDA, cudaGetErrorString(e));
+  const int n = smg::trace_count();
+  unsigned long long origin = ~0ull;
+  for (int i = 0; i < n; i++) origin = std::min(origin, out[2 * i]);
+  std::string all;
+  for (int i = 0; i < n; i++) {
+    t0_us[i] = (out[2 * i] - origin) * 1e-3;
+    t1_us[i] = (out[2 * i + 1] - origin) * 1e-3;
+    all += smg::trace_name(i);
+    all += '\n';
+  }
+  std::snprintf(names, static_cast<size_t>(names_cap), "%s", all.c_str());
+  *n_events = n;
   return SMG_OK;
 }
 

@@ -326,6 +326,16 @@ class Solver:
                                               C.byref(ms), C.byref(nl)))
         return float(ms.value), int(nl.value)
 
+    def trace_iteration(self, k: int = 1, max_events: int = 512):
+        """Device timeline of one solve-loop iteration -> list of (label, start_us, end_us)."""
+        names = C.create_string_buffer(max_events * 64)
+        t0, t1 = np.zeros(max_events), np.zeros(max_events)
+        n = C.c_int(0)
+        self._check(self._lib.smg_trace_iteration(self._h, k, max_events, names, len(names), _dp(t0),
+                                                  _dp(t1), C.byref(n)))
+        labels = names.value.decode().split("\n")[: n.value]
+        return [(labels[i], float(t0[i]), float(t1[i])) for i in range(n.value)]
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.smg_launch_count(self._h))
