@@ -69,7 +69,12 @@ typedef struct smg_options {
   int verbose;    /* 1: print the residual per iteration like the reference (cpp:334,349) */
   int locality_reorder; /* 1: order rows inside a phase by a BFS (Cuthill-McKee) rank (default) */
   int sigma;      /* SELL sort window in rows (default 256; 1 = no length sorting) */
-  int reserved[8];
+  int tail_rows;  /* levels with at most this many rows (and all coarser ones) run inside one
+                     thread-block cluster with cluster barriers instead of one kernel per
+                     dependent step.  Default 0 = off: on B200 a cluster step that exchanges
+                     data through L2 costs ~4 us against ~2.2 us for a PDL-chained kernel
+                     (profiles/ubench/cluster_step.cu); kept as an experiment */
+  int reserved[7];
 } smg_options;
 
 void smg_default_options(smg_options *opt);

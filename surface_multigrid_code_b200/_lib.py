@@ -58,7 +58,8 @@ class smg_options(C.Structure):
         ("verbose", C.c_int),
         ("locality_reorder", C.c_int),
         ("sigma", C.c_int),
-        ("reserved", C.c_int * 8),
+        ("tail_rows", C.c_int),
+        ("reserved", C.c_int * 7),
     ]
 
 

@@ -368,6 +368,164 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
   trace_end(trace_slot);
 }
 
+// ---- cluster tail kernel (see kernels.hpp) --------------------------------------------
+constexpr int kTailThreads = 512;
+constexpr int kTailMaxOps = 96;
+
+__device__ __forceinline__ void cluster_barrier() {
+  // release/acquire at cluster scope: orders the (global-memory) writes of every thread
+  // of the cluster before the reads of every thread that follow the barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// The structure of a row (slice offset, width, columns) is fetched BEFORE the barrier
+// that precedes its step (it is immutable); values, gathers and b are fetched together
+// after it.  kTailRows rows per thread are covered this way; longer steps loop.
+struct TailRow {
+  int w, off;  // off = base + lane
+  int c[kPre];
+};
+
+__device__ __forceinline__ void tail_row_load(TailRow& t, const TailOp& op, int row) {
+  t.w = 0;
+  if (row >= op.pe) return;
+  const int s = row >> 5;
+  const int base = op.slice_ptr[s];
+  t.off = base + (row & 31);
+  t.w = (op.slice_ptr[s + 1] - base) >> 5;
+#pragma unroll
+  for (int j = 0; j < kPre; j++)
+    if (j < t.w) t.c[j] = ld_stream_s32(op.col + t.off + j * 32);
+}
+
+template <int K>
+__device__ __forceinline__ void tail_row_apply(const TailRow& t, const TailOp& op, int row) {
+  const bool gs = op.type == TAIL_GS;
+  double sum[K];
+  double v[kPre];
+  double xv[kPre][K];
+#pragma unroll
+  for (int q = 0; q < K; q++) sum[q] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPre; j++)
+    if (j < t.w && !(gs && t.c[j] == row)) {
+      v[j] = ld_stream_f64(op.val + t.off + j * 32);
+#pragma unroll
+      for (int q = 0; q < K; q++) xv[j][q] = ld_vec(op.x + t.c[j] + (size_t)q * op.ldx);
+    }
+  double bq[K];
+  double d = 1.0;
+  if (gs) d = ld_stream_f64(op.diag + row);
+  if (op.type != TAIL_RESTRICT_ZERO) {
+    const double* bp = op.type == TAIL_PROLONG_ADD ? op.y : op.b;
+#pragma unroll
+    for (int q = 0; q < K; q++) bq[q] = ld_vec(bp + row + (size_t)q * op.ldy);
+  }
+#pragma unroll
+  for (int j = 0; j < kPre; j++)
+    if (j < t.w && !(gs && t.c[j] == row)) {
+#pragma unroll
+      for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v[j], xv[j][q]));
+    }
+  for (int j = kPre; j < t.w; j++) {  // rows longer than the register window
+    const int c = ld_stream_s32(op.col + t.off + j * 32);
+    const double vv = ld_stream_f64(op.val + t.off + j * 32);
+    if (gs && c == row) continue;
+#pragma unroll
+    for (int q = 0; q < K; q++)
+      sum[q] = __dadd_rn(sum[q], __dmul_rn(vv, ld_vec(op.x + c + (size_t)q * op.ldx)));
+  }
+#pragma unroll
+  for (int q = 0; q < K; q++) {
+    const size_t o = row + (size_t)q * op.ldy;
+    switch (op.type) {
+      case TAIL_GS: op.y[o] = __ddiv_rn(__dsub_rn(bq[q], sum[q]), d); break;
+      case TAIL_RESIDUAL: op.y[o] = __dsub_rn(bq[q], sum[q]); break;
+      case TAIL_RESTRICT_ZERO:
+        op.y[o] = sum[q];
+        op.z[o] = 0.0;
+        break;
+      default: op.y[o] = __dadd_rn(bq[q], sum[q]); break;
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kTailThreads, 1)
+tail_kernel(int trace_slot, const TailOp* __restrict__ ops, int nops) {
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  __shared__ TailOp sops[kTailMaxOps];
+  {  // the op list is immutable: stage it (and the first rows' structure) before the PDL wait
+    const int words = nops * (int)(sizeof(TailOp) / sizeof(int));
+    const int* src = reinterpret_cast<const int*>(ops);
+    int* dst = reinterpret_cast<int*>(sops);
+    for (int i = threadIdx.x; i < words; i += kTailThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  // The tail's matrices were last touched one V-cycle leg ago and have usually left L2:
+  // ask for all of them at once (TMA bulk prefetch into L2, one op per CTA round-robin)
+  // so that the dependent steps below pay L2 latency, not DRAM latency.
+  if (threadIdx.x < 32) {
+    for (int i = cluster_ctarank() * 32 + threadIdx.x; i < nops * 3; i += cluster_nctarank() * 32) {
+      const TailOp& op = sops[i / 3];
+      const int part = i % 3;
+      const char* p = nullptr;
+      size_t bytes = 0;
+      if (part == 0) {
+        p = reinterpret_cast<const char*>(op.val + op.ent0);
+        bytes = static_cast<size_t>(op.ent1 - op.ent0) * 8;
+      } else if (part == 1) {
+        p = reinterpret_cast<const char*>(op.col + op.ent0);
+        bytes = static_cast<size_t>(op.ent1 - op.ent0) * 4;
+      } else if (op.type == TAIL_GS) {
+        p = reinterpret_cast<const char*>(op.diag + (op.ps & ~1));
+        bytes = (static_cast<size_t>(op.pe - (op.ps & ~1)) * 8 + 15) & ~static_cast<size_t>(15);
+      }
+      if (bytes > 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p),
+                     "r"(static_cast<uint32_t>(bytes))
+                     : "memory");
+    }
+  }
+  const int gtid = cluster_ctarank() * kTailThreads + threadIdx.x;
+  const int nthreads = cluster_nctarank() * kTailThreads;
+  constexpr int kTailRows = K == 1 ? 3 : 2;
+  TailRow cur[kTailRows];
+#pragma unroll
+  for (int t = 0; t < kTailRows; t++) tail_row_load(cur[t], sops[0], sops[0].ps + gtid + t * nthreads);
+  pdl_wait();
+  for (int i = 0; i < nops; i++) {
+    const TailOp& op = sops[i];
+    int row = op.ps + gtid;
+#pragma unroll
+    for (int t = 0; t < kTailRows; t++, row += nthreads)
+      if (row < op.pe) tail_row_apply<K>(cur[t], op, row);
+    for (; row < op.pe; row += nthreads) {
+      tail_row_load(cur[0], op, row);
+      tail_row_apply<K>(cur[0], op, row);
+    }
+    if (i + 1 < nops) {  // the next step's structure is fetched while the barrier completes
+#pragma unroll
+      for (int t = 0; t < kTailRows; t++)
+        tail_row_load(cur[t], sops[i + 1], sops[i + 1].ps + gtid + t * nthreads);
+      cluster_barrier();
+    }
+  }
+  trace_end(trace_slot);
+}
+
 inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 }  // namespace
@@ -834,6 +992,67 @@ void launch_symmetrize_lower(double* D, int n, cudaStream_t st) {
   dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8);
   symmetrize_lower_kernel<<<g, b, 0, st>>>(D, n);
 }
+namespace {
+template <int K>
+int tail_cluster_size_for() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = 0;
+  cudaFuncSetAttribute(tail_kernel<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  for (int cs : {16, 8, 4, 2, 1}) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(kTailThreads);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, tail_kernel<K>, &cfg) == cudaSuccess &&
+        nclusters >= 1) {
+      cached = cs;
+      break;
+    }
+    cudaGetLastError();
+  }
+  return cached;
+}
+
+template <int K>
+void launch_tail_k(const TailOp* d_ops, int nops, int cluster_size, cudaStream_t st) {
+  int slot = -1;
+  if (g_trace.on && g_trace.next < g_trace.cap) {
+    slot = g_trace.next++;
+    g_trace.names.push_back(g_trace.label + " tail_kernel ops" + std::to_string(nops));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_size);
+  cfg.blockDim = dim3(kTailThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, tail_kernel<K>, slot, d_ops, nops);
+}
+}  // namespace
+
+int tail_cluster_size() { return tail_cluster_size_for<1>(); }
+int tail_max_ops() { return kTailMaxOps; }
+
+void launch_tail(const TailOp* d_ops, int nops, int k, int cluster_size, cudaStream_t st) {
+  if (nops <= 0) return;
+  SMG_DISPATCH_K(k, (tail_cluster_size_for<K>(), launch_tail_k<K>(d_ops, nops, cluster_size, st)));
+}
+
 size_t dense_sym_scratch_doubles(int n, int k) {
   const int nblk = (n + kTile - 1) / kTile;
   return static_cast<size_t>(nblk) * (k < kMaxK ? k : kMaxK) * n;

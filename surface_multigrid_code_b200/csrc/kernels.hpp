@@ -32,6 +32,32 @@ void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, dou
 void set_pdl_enabled(bool on);
 // TMA (cp.async.bulk) staging of the matrix chunks in shared memory (default on)
 void set_tma_enabled(bool on);
+// ---- cluster "tail" kernel ---------------------------------------------------------
+// Levels too small to fill the GPU are latency-bound: a chain of per-phase kernels
+// costs ~2 us per dependent step.  The tail kernel runs a whole list of such steps
+// (Gauss-Seidel phases, residual, restrict, prolong-add of several levels) inside ONE
+// thread-block cluster, separated by cluster barriers (~0.2 us) instead of kernel
+// boundaries.  One op = one dependent step over rows [ps, pe) of a SELL matrix.
+enum TailOpType { TAIL_GS = 0, TAIL_RESIDUAL = 1, TAIL_RESTRICT_ZERO = 2, TAIL_PROLONG_ADD = 3 };
+struct TailOp {
+  int type = 0;
+  int ps = 0, pe = 0;  // rows of M handled by this step
+  int ldx = 0, ldy = 0;
+  int ent0 = 0, ent1 = 0;  // stored entries [ent0, ent1) of col / val belong to rows [ps, pe)
+  const int* slice_ptr = nullptr;
+  const int* col = nullptr;
+  const double* val = nullptr;
+  const double* diag = nullptr;  // TAIL_GS
+  const double* x = nullptr;     // gathered vector (GS: == y)
+  const double* b = nullptr;     // TAIL_GS, TAIL_RESIDUAL
+  double* y = nullptr;           // written vector
+  double* z = nullptr;           // TAIL_RESTRICT_ZERO: zeroed vector
+};
+// cluster size the device accepts for the tail kernel (16, 8, ... or 0 = unsupported)
+int tail_cluster_size();
+int tail_max_ops();
+void launch_tail(const TailOp* d_ops, int nops, int k, int cluster_size, cudaStream_t st);
+
 // in-kernel timeline: slots of 2 x u64 [min start, max end] in nanoseconds (%globaltimer);
 // the caller initialises the buffer to {~0, 0} per slot
 void trace_start(unsigned long long* dev_buf, int cap);

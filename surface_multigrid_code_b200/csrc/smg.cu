@@ -123,6 +123,11 @@ struct LevelDev {
   DevBuf<double> b, u, r;
 };
 
+struct TailLists {
+  DevBuf<smg::TailOp> down, up;
+  int n_down = 0, n_up = 0;
+};
+
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;
@@ -166,6 +171,9 @@ struct smg_handle {
   DevBuf<double> flush;      // L2 flush buffer for smg_time_kernel
 
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+  // cluster tail kernel: first level handled by it (== number of levels - 1: none)
+  int tail_cluster = 0, tail_start = 0;
+  std::map<std::tuple<int, int, int, int, int>, TailLists> tails;  // (first level, pre, post, k0, kk)
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -201,6 +209,109 @@ void drop_graphs(smg_handle* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   h->graphs.clear();
+  h->tails.clear();  // the op lists hold pointers into the work vectors
+}
+
+// first level of the V-cycle started at lv0 that runs inside the cluster tail kernel
+int tail_first_level(const smg_handle* h, int lv0) {
+  const int last = static_cast<int>(h->lv.size()) - 1;
+  if (h->tail_cluster <= 0 || h->opt.tail_rows <= 0) return last;
+  return std::min(last, std::max(lv0, h->tail_start));
+}
+
+smg::TailOp make_op(int type, const SellDev& M, const smg::Sell& host, const double* val, int ps,
+                    int pe) {
+  smg::TailOp op;
+  op.type = type;
+  op.ps = ps;
+  op.pe = pe;
+  op.ent0 = host.slice_ptr[ps >> 5];
+  op.ent1 = host.slice_ptr[std::min(host.nslices, (pe + 31) >> 5)];
+  op.slice_ptr = M.slice_ptr;
+  op.col = M.col;
+  op.val = val;
+  return op;
+}
+
+// op lists of the two legs of the tail (levels ts .. last-1) for columns [k0, k0+kk)
+int prepare_tail(smg_handle* h, int lv0, int pre, int post, int k0, int kk) {
+  const int last = static_cast<int>(h->lv.size()) - 1;
+  const int ts = tail_first_level(h, lv0);
+  if (ts >= last) return SMG_OK;
+  const auto key = std::make_tuple(ts, pre, post, k0, kk);
+  if (h->tails.count(key)) return SMG_OK;
+  std::vector<smg::TailOp> down, up;
+  auto gs_ops = [&](std::vector<smg::TailOp>& out, int l, int iters) {
+    LevelDev& L = h->lv[l];
+    const SellDev A = L.sellA.view();
+    const size_t o = static_cast<size_t>(k0) * L.n;
+    for (int it = 0; it < iters; it++)
+      for (size_t p = 0; p + 1 < L.phase_ptr.size(); p++) {
+        if (L.phase_ptr[p + 1] <= L.phase_ptr[p]) continue;
+        smg::TailOp op = make_op(smg::TAIL_GS, A, h->plan.lv[l].sellA, A.val, L.phase_ptr[p],
+                                 L.phase_ptr[p + 1]);
+        op.diag = L.diag.p;
+        op.x = L.u.p + o;
+        op.b = L.b.p + o;
+        op.y = L.u.p + o;
+        op.ldx = op.ldy = L.n;
+        out.push_back(op);
+      }
+  };
+  for (int l = ts; l < last; l++) {
+    LevelDev& L = h->lv[l];
+    LevelDev& C = h->lv[l + 1];
+    const size_t o = static_cast<size_t>(k0) * L.n, oc = static_cast<size_t>(k0) * C.n;
+    gs_ops(down, l, pre);
+    if (L.n > 0) {
+      const SellDev A = L.sellA.view();
+      smg::TailOp op = make_op(smg::TAIL_RESIDUAL, A, h->plan.lv[l].sellA, A.valT, 0, L.n);
+      op.x = L.u.p + o;
+      op.b = L.b.p + o;
+      op.y = L.r.p + o;
+      op.ldx = op.ldy = L.n;
+      down.push_back(op);
+    }
+    if (C.n > 0) {
+      const SellDev PT = C.sellPT.view();
+      smg::TailOp op = make_op(smg::TAIL_RESTRICT_ZERO, PT, h->plan.lv[l + 1].sellPT, PT.val, 0, C.n);
+      op.x = L.r.p + o;
+      op.ldx = L.n;
+      op.y = C.b.p + oc;
+      op.z = C.u.p + oc;
+      op.ldy = C.n;
+      down.push_back(op);
+    }
+  }
+  for (int l = last - 1; l >= ts; l--) {
+    LevelDev& L = h->lv[l];
+    LevelDev& C = h->lv[l + 1];
+    if (L.n > 0) {
+      const SellDev P = C.sellP.view();
+      smg::TailOp op = make_op(smg::TAIL_PROLONG_ADD, P, h->plan.lv[l + 1].sellP, P.val, 0, L.n);
+      op.x = C.u.p + static_cast<size_t>(k0) * C.n;
+      op.ldx = C.n;
+      op.y = L.u.p + static_cast<size_t>(k0) * L.n;
+      op.ldy = L.n;
+      up.push_back(op);
+    }
+    gs_ops(up, l, post);
+  }
+  TailLists& T = h->tails[key];
+  T.n_down = static_cast<int>(down.size());
+  T.n_up = static_cast<int>(up.size());
+  SMG_CUDA(h, T.down.upload(down, h->stream));
+  SMG_CUDA(h, T.up.upload(up, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMG_OK;
+}
+
+void launch_tail_leg(smg_handle* h, const DevBuf<smg::TailOp>& ops, int n, int kk) {
+  const int cap = smg::tail_max_ops();
+  for (int i = 0; i < n; i += cap) {  // long op lists (wavefront schedules) go out in pieces
+    smg::launch_tail(ops.p + i, std::min(cap, n - i), kk, h->tail_cluster, h->stream);
+    h->launches++;
+  }
 }
 
 int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT) {
@@ -318,8 +429,9 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
 // work vectors lv[l].b / .u of levels l >= lv0.
 void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
   const int last = static_cast<int>(h->lv.size()) - 1;
+  const int ts = tail_first_level(h, lv0);
   char label[32];
-  for (int l = lv0; l < last; l++) {
+  for (int l = lv0; l < ts; l++) {
     LevelDev& L = h->lv[l];
     LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d down", l);
@@ -328,10 +440,28 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
     restrict_device(h, l, L.r.p, C.b.p, k, C.u.p);         // :44 and uc = 0 (:46-47), fused
   }
+  if (ts < last) {  // levels ts .. last-1, down leg, inside one cluster
+    std::snprintf(label, sizeof(label), "L%d-%d down", ts, last - 1);
+    smg::trace_label(label);
+    for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+      const int kk = std::min(smg::kMaxK, k - k0);
+      const TailLists& T = h->tails.at(std::make_tuple(ts, pre, post, k0, kk));
+      launch_tail_leg(h, T.down, T.n_down, kk);
+    }
+  }
   std::snprintf(label, sizeof(label), "L%d", last);
   smg::trace_label(label);
   coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
-  for (int l = last - 1; l >= lv0; l--) {
+  if (ts < last) {
+    std::snprintf(label, sizeof(label), "L%d-%d up", ts, last - 1);
+    smg::trace_label(label);
+    for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+      const int kk = std::min(smg::kMaxK, k - k0);
+      const TailLists& T = h->tails.at(std::make_tuple(ts, pre, post, k0, kk));
+      launch_tail_leg(h, T.up, T.n_up, kk);
+    }
+  }
+  for (int l = ts - 1; l >= lv0; l--) {
     LevelDev& L = h->lv[l];
     std::snprintf(label, sizeof(label), "L%d up", l);
     smg::trace_label(label);
@@ -341,6 +471,8 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
 }
 
 int vcycle_run(smg_handle* h, int lv0, int pre, int post, int k) {
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK)
+    SMG_TRY(prepare_tail(h, lv0, pre, post, k0, std::min(smg::kMaxK, k - k0)));
   if (!h->opt.use_graph) {
     vcycle_device(h, lv0, pre, post, k);
     return check_launch(h, "vcycle");
@@ -518,6 +650,8 @@ int upload_plan(smg_handle* h) {
       h->launches += 2;
     }
   }
+  h->tail_start = nlev - 1;
+  for (int l = nlev - 2; l >= 0 && pl.lv[l].n <= h->opt.tail_rows; l--) h->tail_start = l;
   SMG_CUDA(h, h->lhs_src.upload(pl.lhs_src, st));
   // permuted unknown row -> caller index
   const std::vector<int>& perm0 = pl.lv[0].order.perm;
@@ -711,6 +845,7 @@ void smg_default_options(smg_options* opt) {
   opt->verbose = 0;
   opt->locality_reorder = 1;
   opt->sigma = 256;
+  opt->tail_rows = 0;  // measured slower than the PDL kernel chain on B200, see DESIGN.md section 4
 }
 
 int smg_version(void) { return SMG_VERSION; }
@@ -767,6 +902,8 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   }
   h->device = dev;
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
+  if (const char* e = std::getenv("SMG_TAIL_ROWS")) h->opt.tail_rows = std::atoi(e);
+  h->tail_cluster = h->opt.tail_rows > 0 ? smg::tail_cluster_size() : 0;
   if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 64 * sizeof(double)) != cudaSuccess) {
@@ -1242,6 +1379,8 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
   // the traced graph is built with the trace slots baked in and never cached
   SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
   SMG_CUDA(h, h->norm_out.reserve(4));
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK)
+    SMG_TRY(prepare_tail(h, 0, h->opt.pre_relax, h->opt.post_relax, k0, std::min(smg::kMaxK, k - k0)));
   smg::trace_start(buf.p, max_events);
   smg::trace_label("norm");
   cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);

@@ -63,7 +63,7 @@ class Solver:
 
     def __init__(self, smoother: str = "multicolour", device=None, use_graph: bool = True,
                  pre_relax: int = 2, post_relax: int = 2, verbose: bool = False,
-                 locality_reorder: bool = True, sigma: int = 256):
+                 locality_reorder: bool = True, sigma: int = 256, tail_rows: Optional[int] = None):
         self._lib = L.load()
         opt = L.smg_options()
         self._lib.smg_default_options(C.byref(opt))
@@ -81,6 +81,8 @@ class Solver:
         opt.verbose = int(bool(verbose))
         opt.locality_reorder = int(bool(locality_reorder))
         opt.sigma = int(sigma)
+        if tail_rows is not None:
+            opt.tail_rows = int(tail_rows)
         self.smoother = smoother
         self.plan_only = device == "none"
         self._h = L._vp()
