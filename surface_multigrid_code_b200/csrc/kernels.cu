@@ -800,7 +800,7 @@ constexpr int kTile = 64;
 
 template <int K>
 __global__ void __launch_bounds__(256)
-dense_sym_tile_kernel(int trace_slot, const double* __restrict__ Ainv, const double* b,
+dense_sym_tile_kernel(int trace_slot, const double* __restrict__ tiles, const double* b,
                       double* __restrict__ partial, int n, int ldb) {
   trace_begin(trace_slot);
   pdl_launch_dependents();
@@ -813,12 +813,27 @@ dense_sym_tile_kernel(int trace_slot, const double* __restrict__ Ainv, const dou
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = I * kTile + lane, r1 = r0 + 32;
   const int c0 = J * kTile + warp * 8;
+  // The launch is programmatic: the first CTAs start long before the coarse right-hand
+  // side exists (while the latency-bound coarse levels run and HBM idles).  They ask for
+  // ALL tiles to be brought into L2 (TMA bulk prefetch), so the CTAs that only become
+  // resident after the PDL wait stream from L2 instead of DRAM.
+  constexpr int kPrefetchers = 512;
+  if (threadIdx.x == 0 && t < kPrefetchers) {
+    for (int tt = t + kPrefetchers; tt < (int)gridDim.x; tt += kPrefetchers) {
+      const double* p = tiles + static_cast<size_t>(tt) * (kTile * kTile);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p),
+                   "r"(static_cast<uint32_t>(kTile * kTile * sizeof(double)))
+                   : "memory");
+    }
+  }
   double m0[8], m1[8];
+  // tile t is one contiguous 32 KB block (column-major inside, zero beyond n); it is
+  // immutable during a solve and fetched before the PDL wait
+  const double* tp = tiles + static_cast<size_t>(t) * (kTile * kTile) + (warp * 8) * kTile + lane;
 #pragma unroll
-  for (int c = 0; c < 8; c++) {  // immutable during a solve: fetched before the PDL wait
-    const size_t col = static_cast<size_t>(c0 + c) * n;
-    m0[c] = (c0 + c < n && r0 < n) ? ld_stream_f64(Ainv + col + r0) : 0.0;
-    m1[c] = (c0 + c < n && r1 < n) ? ld_stream_f64(Ainv + col + r1) : 0.0;
+  for (int c = 0; c < 8; c++) {
+    m0[c] = ld_stream_f64(tp + c * kTile);
+    m1[c] = ld_stream_f64(tp + c * kTile + 32);
   }
   pdl_wait();
   __shared__ double red[8][kTile];
@@ -860,29 +875,52 @@ dense_sym_tile_kernel(int trace_slot, const double* __restrict__ Ainv, const dou
   trace_end(trace_slot);
 }
 
+// u[block-row X] += sum over the nblk slots, in slot order: 64 rows x 4 slot groups per CTA
 template <int K>
 __global__ void __launch_bounds__(256)
 dense_sym_reduce_kernel(int trace_slot, const double* partial, double* u, int n, int nblk, int ldu) {
   trace_begin(trace_slot);
   pdl_launch_dependents();
   pdl_wait();
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) {
+  __shared__ double red[4][kTile];
+  const int r = threadIdx.x & (kTile - 1), g = threadIdx.x >> 6;
+  const int i = blockIdx.x * kTile + r;
 #pragma unroll
-    for (int q = 0; q < K; q++) {
-      double sum = 0.0;
-      for (int s0 = 0; s0 < nblk; s0 += 16) {  // 16 independent loads in flight, summed in order
-        double v[16];
-#pragma unroll
-        for (int t = 0; t < 16; t++)
-          v[t] = s0 + t < nblk ? ld_vec(partial + (static_cast<size_t>(s0 + t) * K + q) * n + i) : 0.0;
-#pragma unroll
-        for (int t = 0; t < 16; t++) sum += v[t];
-      }
-      u[i + static_cast<size_t>(q) * ldu] = ld_vec(u + i + static_cast<size_t>(q) * ldu) + sum;
+  for (int q = 0; q < K; q++) {
+    double sum = 0.0;
+    if (i < n)
+      for (int s = g; s < nblk; s += 4) sum += ld_vec(partial + (static_cast<size_t>(s) * K + q) * n + i);
+    red[g][r] = sum;
+    __syncthreads();
+    if (g == 0 && i < n) {
+      const double tot = ((red[0][r] + red[1][r]) + red[2][r]) + red[3][r];
+      u[i + static_cast<size_t>(q) * ldu] = ld_vec(u + i + static_cast<size_t>(q) * ldu) + tot;
     }
+    __syncthreads();
   }
   trace_end(trace_slot);
+}
+
+// pack the lower-triangular 64x64 tiles of a symmetric matrix whose LOWER triangle is valid
+// (cusolver potri output) into contiguous tiles, mirroring inside the diagonal tiles
+__global__ void __launch_bounds__(256)
+pack_sym_tiles_kernel(const double* __restrict__ A, double* __restrict__ tiles, int n) {
+  const int t = blockIdx.x;
+  int I = static_cast<int>((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+  while ((I + 1) * (I + 2) / 2 <= t) I++;
+  while (I * (I + 1) / 2 > t) I--;
+  const int J = t - I * (I + 1) / 2;
+  for (int e = threadIdx.x; e < kTile * kTile; e += 256) {
+    const int c = e / kTile, r = e % kTile;
+    int gr = I * kTile + r, gc = J * kTile + c;
+    if (gr < gc) {  // only inside a diagonal tile: take the mirrored entry
+      const int tmp = gr;
+      gr = gc;
+      gc = tmp;
+    }
+    tiles[static_cast<size_t>(t) * (kTile * kTile) + e] =
+        (gr < n && gc < n) ? A[static_cast<size_t>(gc) * n + gr] : 0.0;
+  }
 }
 
 __global__ void gather_system_kernel(const double* __restrict__ RHS,
@@ -1064,8 +1102,17 @@ void launch_dense_sym_add(const double* Ainv, const double* b, double* u, double
   const int ntiles = nblk * (nblk + 1) / 2;
   SMG_DISPATCH_K(k, launch_kernel("coarse_tiles", dense_sym_tile_kernel<K>, ntiles, 256, 0, st, Ainv,
                                   b, scratch, n, n));
-  SMG_DISPATCH_K(k, launch_kernel("coarse_reduce", dense_sym_reduce_kernel<K>, blocks_for(n, 256),
-                                  256, 0, st, scratch, u, n, nblk, n));
+  SMG_DISPATCH_K(k, launch_kernel("coarse_reduce", dense_sym_reduce_kernel<K>, nblk, 256, 0, st,
+                                  scratch, u, n, nblk, n));
+}
+size_t dense_sym_tiles_doubles(int n) {
+  const size_t nblk = (n + kTile - 1) / kTile;
+  return nblk * (nblk + 1) / 2 * kTile * kTile;
+}
+void launch_pack_sym_tiles(const double* A_lower, double* tiles, int n, cudaStream_t st) {
+  if (n <= 0) return;
+  const int nblk = (n + kTile - 1) / kTile;
+  pack_sym_tiles_kernel<<<nblk * (nblk + 1) / 2, 256, 0, st>>>(A_lower, tiles, n);
 }
 void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
                            cudaStream_t st) {

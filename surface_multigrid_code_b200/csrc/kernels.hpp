@@ -107,10 +107,12 @@ void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const do
                          const int* iperm, double* D, int n, cudaStream_t st);
 // mirror the lower triangle of a column-major n x n matrix into the upper one
 void launch_symmetrize_lower(double* D, int n, cudaStream_t st);
-// u = u + Ainv * b reading only the lower-triangular 64x64 tiles of the symmetric Ainv;
-// scratch must hold dense_sym_scratch_doubles(n, k) doubles
+// u = u + Ainv * b from the packed lower-triangular 64x64 tiles of the symmetric Ainv
+// (launch_pack_sym_tiles); scratch must hold dense_sym_scratch_doubles(n, k) doubles
 size_t dense_sym_scratch_doubles(int n, int k);
-void launch_dense_sym_add(const double* Ainv, const double* b, double* u, double* scratch, int n,
+size_t dense_sym_tiles_doubles(int n);
+void launch_pack_sym_tiles(const double* A_lower, double* tiles, int n, cudaStream_t st);
+void launch_dense_sym_add(const double* tiles, const double* b, double* u, double* scratch, int n,
                           int k, cudaStream_t st);
 // u = u + Ainv * b  (Ainv symmetric dense n x n; b,u: n x k), one warp per full row
 void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,

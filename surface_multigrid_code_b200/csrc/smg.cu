@@ -160,7 +160,7 @@ struct smg_handle {
   int n_known_distinct = 0;
 
   // coarse direct solve
-  DevBuf<double> ainv, coarse_scratch;
+  DevBuf<double> ainv, ainv_tiles, coarse_scratch;
   DevBuf<double> potrf_work;
   DevBuf<int> dev_info;
 
@@ -420,7 +420,7 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L.n;
-    smg::launch_dense_sym_add(h->ainv.p, b + o, u + o, h->coarse_scratch.p, L.n, kk, h->stream);
+    smg::launch_dense_sym_add(h->ainv_tiles.p, b + o, u + o, h->coarse_scratch.p, L.n, kk, h->stream);
     h->launches += 2;
   }
 }
@@ -598,7 +598,9 @@ int numeric_setup(smg_handle* h) {
       return fail(h, SMG_E_CUSOLVER,
                   "coarsest matrix is not positive definite (potrf info " +
                       std::to_string(info[0]) + ", potri info " + std::to_string(info[1]) + ")");
-    smg::launch_symmetrize_lower(h->ainv.p, nc, st);
+    // keep only the packed lower tiles (half the bytes, contiguous 32 KB blocks)
+    SMG_CUDA(h, h->ainv_tiles.reserve(smg::dense_sym_tiles_doubles(nc)));
+    smg::launch_pack_sym_tiles(h->ainv.p, h->ainv_tiles.p, nc, st);
     h->launches++;
     SMG_TRY(check_launch(h, "coarse inverse"));
   }
@@ -932,7 +934,7 @@ void smg_destroy(smg_handle* h) {
     h->a_in.release(); h->lhs_src.release(); h->auk_src.release(); h->g.release();
     h->auk_ptr.release(); h->auk_q.release(); h->auk_pos.release();
     h->auk_csc_val.release(); h->auk_val.release(); h->kidx.release(); h->ksrc.release();
-    h->ainv.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
+    h->ainv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
     h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
     if (h->stream) cudaStreamDestroy(h->stream);
