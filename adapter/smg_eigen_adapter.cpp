@@ -322,6 +322,21 @@ template bool min_quad_with_fixed_mg_solve<MatrixXd, MatrixXd, MatrixXd, MatrixX
     const min_quad_with_fixed_mg_data&, const SMG_PB(MatrixXd)&, const SMG_PB(MatrixXd)&,
     const SMG_PB(MatrixXd)&, const LDLT&, const double&, std::vector<mg_data>&, SMG_PB(MatrixXd)&,
     std::vector<double>&);
+// a superset: the (tolerance, maxIter) overloads, which the reference only reaches internally
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&, const LDLT&,
+    const double&, const int&, std::vector<mg_data>&, SMG_PB(VectorXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<MatrixXd, MatrixXd, MatrixXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(MatrixXd)&, const SMG_PB(MatrixXd)&, const LDLT&,
+    const double&, const int&, std::vector<mg_data>&, SMG_PB(MatrixXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<VectorXd, VectorXd, VectorXd, VectorXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(VectorXd)&, const SMG_PB(VectorXd)&,
+    const SMG_PB(VectorXd)&, const LDLT&, const double&, const int&, std::vector<mg_data>&,
+    SMG_PB(VectorXd)&, std::vector<double>&);
+template bool min_quad_with_fixed_mg_solve<MatrixXd, MatrixXd, MatrixXd, MatrixXd>(
+    const min_quad_with_fixed_mg_data&, const SMG_PB(MatrixXd)&, const SMG_PB(MatrixXd)&,
+    const SMG_PB(MatrixXd)&, const LDLT&, const double&, const int&, std::vector<mg_data>&,
+    SMG_PB(MatrixXd)&, std::vector<double>&);
 template void mg_VCycle<VectorXd, VectorXd>(const LDLT&, const SMG_PB(VectorXd)&, const int&, const int&,
                                             const int, SMG_PB(VectorXd)&, std::vector<mg_data>&);
 template void mg_VCycle<MatrixXd, MatrixXd>(const LDLT&, const SMG_PB(MatrixXd)&, const int&, const int&,

@@ -199,7 +199,9 @@ typedef enum smg_kernel_id {
   SMG_K_VCYCLE = 6,     /* one full V-cycle from level 0 (graph when enabled) */
   /* one iteration of the solve loop (min_quad_with_fixed_mg.cpp:330-347): residual
    * norm with its host read-back, then one V-cycle */
-  SMG_K_MG_ITERATION = 7
+  SMG_K_MG_ITERATION = 7,
+  /* the pre-smoothing of a V-cycle: opt.pre_relax Gauss-Seidel sweeps back to back */
+  SMG_K_RELAX_PRE = 8
 } smg_kernel_id;
 int smg_time_kernel(smg_handle *h, int which, int lv, int k, int reps, int flush_l2,
                     float *ms_per_rep, int *launches_per_rep);

@@ -45,6 +45,7 @@ KERNEL = {
     "coarse_solve": 5,
     "vcycle": 6,
     "mg_iteration": 7,
+    "relax_pre": 8,
 }
 
 

@@ -158,7 +158,7 @@ struct RowView {
 // return pointers into shared memory; otherwise pointers into the global SELL arrays.
 // Must be called by every thread of the CTA (contains __syncthreads); the caller waits
 // with stage_wait() after its PDL wait.
-template <bool STAGED>
+template <bool STAGED, int NSL = kSlices>
 __device__ __forceinline__ RowView stage_rows(int slice0, int nslices, int row, bool active,
                                               const int* __restrict__ slice_ptr,
                                               const int* __restrict__ col,
@@ -180,7 +180,7 @@ __device__ __forceinline__ RowView stage_rows(int slice0, int nslices, int row, 
     const int e0 = slice_ptr[slice0];
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
-      const int s1 = slice0 + kSlices < nslices ? slice0 + kSlices : nslices;
+      const int s1 = slice0 + NSL < nslices ? slice0 + NSL : nslices;
       const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - e0);
       const uint64_t pol = l2_evict_first_policy();
       mbar_expect_tx(bar, nent * 12u);
@@ -267,6 +267,91 @@ sell_apply_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const i
       if (MODE == MODE_ADD) y[o] = __dadd_rn(ld_vec(y + o), sum[q]);
       if (MODE == MODE_SPMV_ZERO) {
         y[o] = sum[q];
+        z[o] = 0.0;
+      }
+    }
+  }
+  trace_end(trace_slot);
+}
+
+// Transfer operators have very short rows (a prolongation row holds at most three
+// entries): one row per thread makes CTAs that move only a few KB each and the kernel
+// becomes bound by CTA turnover.  Here a thread owns R rows (256 apart inside the CTA's
+// R*8 slices, staged by ONE bulk copy); all gathers of all its rows are issued before
+// the first sum.  Requires every slice to be at most W wide.
+template <int K, int MODE, int R, int W>
+__global__ void __launch_bounds__(kBlock)
+sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
+                        const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                        const double* __restrict__ val, const double* x, int ldx, double* y,
+                        int ldy, double* z) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  const int slice0 = blockIdx.x * (kSlices * R);
+  const int row0 = blockIdx.x * (kBlock * R) + threadIdx.x;
+  double* sval = reinterpret_cast<double*>(dyn);
+  int* scol = reinterpret_cast<int*>(dyn + (size_t)max_chunk * sizeof(double));
+  const int e0 = slice_ptr[slice0];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    const int s1 = slice0 + kSlices * R < nslices ? slice0 + kSlices * R : nslices;
+    const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - e0);
+    const uint64_t pol = l2_evict_first_policy();
+    mbar_expect_tx(&bar, nent * 12u);
+    if (nent > 0) {
+      bulk_g2s(sval, val + e0, nent * 8u, &bar, pol);
+      bulk_g2s(scol, col + e0, nent * 4u, &bar, pol);
+    }
+  }
+  int off[R], w[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row = row0 + r * kBlock;
+    w[r] = 0;
+    off[r] = 0;
+    if (row < nrows) {
+      const int s = row >> 5;
+      const int base = slice_ptr[s];
+      w[r] = (slice_ptr[s + 1] - base) >> 5;
+      off[r] = base - e0 + (row & 31);
+    }
+  }
+  __syncthreads();
+  pdl_wait();
+  mbar_wait(&bar, 0);
+  double xv[R][W][K], vv[R][W], yv[R][K];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (j < w[r]) {
+        const int c = scol[off[r] + j * 32];
+        vv[r][j] = sval[off[r] + j * 32];
+#pragma unroll
+        for (int q = 0; q < K; q++) xv[r][j][q] = ld_vec(x + c + (size_t)q * ldx);
+      }
+    if (MODE == MODE_ADD && row0 + r * kBlock < nrows) {
+#pragma unroll
+      for (int q = 0; q < K; q++) yv[r][q] = ld_vec(y + row0 + r * kBlock + (size_t)q * ldy);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row = row0 + r * kBlock;
+    if (row >= nrows) continue;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < W; j++)
+        if (j < w[r]) sum = __dadd_rn(sum, __dmul_rn(vv[r][j], xv[r][j][q]));
+      const size_t o = row + (size_t)q * ldy;
+      if (MODE == MODE_SPMV) y[o] = sum;
+      if (MODE == MODE_ADD) y[o] = __dadd_rn(yv[r][q], sum);
+      if (MODE == MODE_SPMV_ZERO) {
+        y[o] = sum;
         z[o] = 0.0;
       }
     }
@@ -563,6 +648,16 @@ template <int MODE>
 void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, const double* b,
                   double* y, int ldy, double* z, int k, cudaStream_t st) {
   if (M.nrows <= 0) return;
+  constexpr int R = 4, W = 3;
+  if (MODE != MODE_RESIDUAL && g_use_tma && M.max_width <= W && M.max_chunk32 > 0 &&
+      static_cast<size_t>(M.max_chunk32) * 12 <= static_cast<size_t>(kStageCapBytes)) {
+    const int gs = blocks_for(M.nrows, kBlock * R);
+    constexpr int SM = MODE == MODE_RESIDUAL ? MODE_SPMV : MODE;  // (never instantiated for residual)
+    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<K, SM, R, W>, gs, kBlock,
+                                    static_cast<size_t>(M.max_chunk32) * 12, st, M.nrows, M.nslices,
+                                    M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, y, ldy, z));
+    return;
+  }
   const int g = blocks_for(M.nrows, kBlock);
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, true>, g, kBlock, stage_bytes(M), st,

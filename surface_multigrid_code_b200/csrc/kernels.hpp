@@ -14,6 +14,8 @@ struct SellDev {
   int nrows = 0;
   int nslices = 0;
   int max_chunk = 0;  // most stored entries in any 8 consecutive slices (one CTA's chunk)
+  int max_width = 0;  // widest slice (entries per row)
+  int max_chunk32 = 0;  // most stored entries in any aligned group of 32 slices
   const int* slice_ptr = nullptr;
   const int* col = nullptr;
   const double* val = nullptr;

@@ -89,13 +89,15 @@ struct DevBuf {
 struct SellBufs {
   DevBuf<int> slice_ptr, col, src;
   DevBuf<double> val, valT;
-  int nrows = 0, nslices = 0, max_chunk = 0;
+  int nrows = 0, nslices = 0, max_chunk = 0, max_width = 0, max_chunk32 = 0;
   int64_t padded = 0;
   SellDev view() const {
     SellDev d;
     d.nrows = nrows;
     d.nslices = nslices;
     d.max_chunk = max_chunk;
+    d.max_width = max_width;
+    d.max_chunk32 = max_chunk32;
     d.slice_ptr = slice_ptr.p;
     d.col = col.p;
     d.val = val.p;
@@ -318,10 +320,14 @@ int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT
   out->nrows = S.nrows;
   out->nslices = S.nslices;
   out->padded = S.padded();
-  out->max_chunk = 0;
+  out->max_chunk = out->max_width = out->max_chunk32 = 0;
   for (int s0 = 0; s0 < S.nslices; s0++) {  // any 8 consecutive slices: one CTA's TMA chunk
     const int s1 = std::min(S.nslices, s0 + 8);
     out->max_chunk = std::max(out->max_chunk, S.slice_ptr[s1] - S.slice_ptr[s0]);
+    out->max_width = std::max(out->max_width, (S.slice_ptr[s0 + 1] - S.slice_ptr[s0]) / 32);
+    if (s0 % 32 == 0)
+      out->max_chunk32 = std::max(out->max_chunk32,
+                                  S.slice_ptr[std::min(S.nslices, s0 + 32)] - S.slice_ptr[s0]);
   }
   SMG_CUDA(h, out->slice_ptr.upload(S.slice_ptr, h->stream));
   SMG_CUDA(h, out->col.upload(S.col, h->stream));
@@ -1315,6 +1321,7 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
     switch (which) {
       case SMG_K_RESIDUAL: residual_device(h, lv, L.b.p, L.u.p, L.r.p, k); break;
       case SMG_K_RELAX_SWEEP: relax_device(h, lv, 1, L.b.p, L.u.p, k); break;
+      case SMG_K_RELAX_PRE: relax_device(h, lv, h->opt.pre_relax, L.b.p, L.u.p, k); break;
       case SMG_K_RESTRICT: restrict_device(h, lv, L.r.p, h->lv[lv + 1].b.p, k); break;
       case SMG_K_PROLONG_ADD: prolong_device(h, lv, h->lv[lv + 1].u.p, L.u.p, k, true); break;
       case SMG_K_RESIDUAL_NORM: {

@@ -440,3 +440,109 @@ def grid_mesh(nx: int, ny: int, jitter: float = 0.0, seed: int = 0):
             fs.append((a, a + 1, a + nx + 1))
             fs.append((a, a + nx + 1, a + nx))
     return V, np.asarray(fs, dtype=np.int32)
+
+
+# --------------------------------------------------------------------------- #
+# stand-in hierarchy for arbitrary meshes (NOT the reference's SSP decimation)
+# --------------------------------------------------------------------------- #
+def mis_hierarchy(V: np.ndarray, F: np.ndarray, n_levels: int, pad_three: bool = True):
+    """Prolongations for an arbitrary triangle mesh without the reference's hierarchy
+    builder (mg_precompute needs Eigen and stays out of scope).
+
+    Coarse vertices = a greedy maximal independent set of the level's graph; a fine vertex
+    interpolates from its (up to three) nearest coarse neighbours with inverse-distance
+    weights.  The result has the layout the hot path relies on (get_prolong.cpp:45-56):
+    non-negative rows summing to one, at most -- with ``pad_three`` exactly, where three
+    coarse vertices are in reach -- three stored entries per row, explicit zeros kept.
+    The coarse graph is the pattern of P^T G P.  Returns [P_1, ..., P_{n_levels-1}].
+    """
+    n = V.shape[0]
+    ij = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]], axis=0).astype(np.int64)
+    G = sp.coo_matrix((np.ones(ij.shape[0]), (ij[:, 0], ij[:, 1])), shape=(n, n)).tocsr()
+    G = ((G + G.T) > 0).astype(np.float64).tocsr()
+    X = np.asarray(V, dtype=np.float64)
+    Ps = []
+    for _ in range(n_levels - 1):
+        nf = G.shape[0]
+        indptr, indices = G.indptr, G.indices
+        state = np.zeros(nf, dtype=np.int8)  # 0 undecided, 1 coarse, 2 fine
+        for i in np.argsort(-np.diff(indptr), kind="stable"):  # high degree first
+            if state[i] == 0:
+                state[i] = 1
+                nb = indices[indptr[i]:indptr[i + 1]]
+                state[nb[state[nb] == 0]] = 2
+        coarse = np.nonzero(state == 1)[0]
+        cid = np.full(nf, -1, dtype=np.int64)
+        cid[coarse] = np.arange(coarse.size)
+        rows, cols, vals = [], [], []
+        agg = np.zeros(nf, dtype=np.int64)  # nearest coarse vertex: the aggregate of i
+        for i in range(nf):
+            if state[i] == 1:
+                cand = [(0.0, i)]
+            else:
+                cand = []
+            nb = indices[indptr[i]:indptr[i + 1]]
+            seen = {int(i)}
+            for j in nb:  # coarse vertices in the 1-ring and 2-ring
+                for jj in [j] + list(indices[indptr[j]:indptr[j + 1]]):
+                    jj = int(jj)
+                    if state[jj] == 1 and jj not in seen:
+                        seen.add(jj)
+                        cand.append((float(np.linalg.norm(X[i] - X[jj])), jj))
+            cand.sort()
+            cand = cand[:3]
+            agg[i] = cid[cand[0][1]]
+            if state[i] == 1:
+                w = [1.0] + [0.0] * (len(cand) - 1)
+            else:
+                inv = np.array([1.0 / max(d, 1e-300) for d, _ in cand])
+                w = list(inv / inv.sum())
+            if not pad_three:
+                keep = [t for t in range(len(cand)) if w[t] != 0.0]
+                cand, w = [cand[t] for t in keep], [w[t] for t in keep]
+            for (d, j), wt in zip(cand, w):
+                rows.append(i)
+                cols.append(cid[j])
+                vals.append(wt)
+        P = csc_keep_zeros(rows, cols, vals, (nf, coarse.size))
+        Ps.append(P)
+        # coarse graph: two aggregates are adjacent when a fine edge joins them
+        Pb = sp.csr_matrix((np.ones(nf), (np.arange(nf), agg)), shape=(nf, coarse.size))
+        Gc = (Pb.T @ G @ Pb).tocsr()
+        Gc.setdiag(0)
+        Gc.eliminate_zeros()
+        G = (Gc > 0).astype(np.float64).tocsr()
+        X = X[coarse]
+    return Ps
+
+
+def mesh_problem(name: str, V, F, n_levels: int, tol=1e-3, max_iter=20, pad_three=True) -> Problem:
+    """03_mg_solver/main.cpp on an arbitrary mesh: unit-area normalisation, A = -cotmatrix,
+    longest boundary loop pinned to 0 (vertex 0 if closed), b = voronoi mass, z0 = 0, with
+    the stand-in hierarchy of ``mis_hierarchy``."""
+    V = normalize_unit_area(V, F)
+    known = boundary_loop(F)
+    if known.size == 0:
+        known = np.array([0], dtype=np.int32)
+    P = mis_hierarchy(V, F, n_levels, pad_three=pad_three)
+    return poisson_problem(name, V, F, P, known, tol, max_iter)
+
+
+def write_problem_file(path: str, pr: Problem):
+    """Flat binary hand-over of a (k = 1, fixed-variant) problem to the headless C++
+    examples: int32 header {magic 'SMG1', levels, n, nknown}; A then every P_full as
+    {rows, cols, nnz, colptr[cols+1], rowidx[nnz], val[nnz]}; known[nknown] (int32),
+    known_val, rhs, z0 (float64)."""
+    assert pr.k == 1 and pr.known is not None
+    with open(path, "wb") as fh:
+        np.array([0x534D4731, pr.nlev, pr.n, pr.known.size], dtype=np.int32).tofile(fh)
+        for m in [pr.A] + list(pr.P):
+            m = m.tocsc()
+            np.array([m.shape[0], m.shape[1], m.nnz], dtype=np.int32).tofile(fh)
+            m.indptr.astype(np.int32).tofile(fh)
+            m.indices.astype(np.int32).tofile(fh)
+            m.data.astype(np.float64).tofile(fh)
+        pr.known.astype(np.int32).tofile(fh)
+        np.asarray(pr.known_val, dtype=np.float64).tofile(fh)
+        np.asarray(pr.rhs, dtype=np.float64).tofile(fh)
+        np.asarray(pr.z0, dtype=np.float64).tofile(fh)

@@ -68,6 +68,17 @@ def main():
     H = Hierarchy(pr.A, pr.P, None)
     z, r, ok = H.solve(pr.rhs, pr.z0, None, pr.tol, pr.max_iter)
     np.savez_compressed(os.path.join(HERE, "mcf_s3_l3.npz"), **pack(pr, z, r, ok, H))
+    # BASELINE configs 1-2: 03_mg_solver Poisson on the reference's own meshes (bunny.obj,
+    # ogre.obj) with the stand-in MIS hierarchy (the reference's SSP hierarchy needs Eigen).
+    # Only possible where /root/reference is mounted; the .npz travels to the GPU box.
+    mesh_dir = "/root/reference/meshes"
+    if os.path.isdir(mesh_dir):
+        for name, nlev in (("bunny", 3), ("ogre", 4)):
+            V, F = mg.read_obj(os.path.join(mesh_dir, name + ".obj"))
+            pr = mg.mesh_problem(name, V, F, nlev, tol=1e-3, max_iter=20)
+            H = Hierarchy(pr.A, pr.P, pr.known)
+            z, r, ok = H.solve(pr.rhs, pr.z0, pr.known_val, pr.tol, pr.max_iter)
+            np.savez_compressed(os.path.join(HERE, f"{name}_l{nlev}.npz"), **pack(pr, z, r, ok, H))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import scipy.sparse as sp
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["sphere_s3_l3", "grid_s2_l3", "mcf_s3_l3"]
+NAMES = ["sphere_s3_l3", "grid_s2_l3", "mcf_s3_l3", "bunny_l3", "ogre_l4"]
 
 
 def load(name):
