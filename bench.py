@@ -319,7 +319,7 @@ def run_gpu(args):
     try:
         prev_end, acc = 0.0, {}
         for name, t0, t1 in s.trace_iteration(k):
-            key = name.split(" g")[0]
+            key = name.rsplit(" g", 1)[0]
             acc[key] = acc.get(key, 0.0) + (t1 - max(t0, prev_end))
             prev_end = max(prev_end, t1)
         gs_us = acc.get("L0 down gs_phase", 0.0) + acc.get("L0 up gs_phase", 0.0)

@@ -183,6 +183,11 @@ int smg_level_padded_nnz(const smg_handle *h, int lv, int64_t *padded);
  *  [7] smoother phases */
 int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
 
+/* dataflow smoother schedule of level lv, out[4]: [0] row blocks (CTAs per sweep)
+ * [1] sum over blocks of the blocks of other phases they wait for [2] the maximum
+ * [3] 1 if the dataflow schedule is used on this level */
+int smg_level_dep_stats(const smg_handle *h, int lv, int64_t *out);
+
 /* ---- measurement ----------------------------------------------------------
  * Times `reps` back-to-back launches of one hot-path kernel on level lv with k
  * right-hand sides using CUDA events on the handle's stream; returns the mean

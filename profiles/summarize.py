@@ -62,17 +62,28 @@ def full_capture():
 
 
 ll, fc = launch_list(), full_capture()
-traffic = {}
+
+
+def to_bytes(text, unit):
+    v = float(text.replace(",", ""))
+    return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+
+
 if fc:
-    def mb(rec, key):
-        v = float(rec[key].replace(",", ""))
-        return v
-    gs = [r for r in fc if "gs_phase" in r["Kernel Name"]]
-    if gs:
-        # one sweep = the distinct colour launches; dram bytes per launch from the capture
-        hdr_r, hdr_w = "dram__bytes_read.sum", "dram__bytes_write.sum"
-        traffic["gs_phase_launches_captured"] = len(gs)
-        traffic["note"] = "units as printed by ncu in the *_full.md table"
+    # DRAM traffic of one fine-level Gauss-Seidel sweep = the first four level-0 colour launches
+    rep = f"{OUT}/prof_{tag}.ncu-rep"
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik, ig = (hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"),
+                      hdr.index("Kernel Name"), hdr.index("Grid Size"))
+    gs = [r for r in rows[2:] if "gs_phase" in r[ik]]
+    big = max(int(r[ig].strip("()").split(",")[0]) for r in gs)
+    lvl0 = [r for r in gs if int(r[ig].strip("()").split(",")[0]) >= big - 1][:4]
+    sweep = sum(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in lvl0)
+    json.dump({"relax_sweep_dram_bytes": sweep, "launches_in_sweep": len(lvl0), "source": f"profiles/{tag}_full.md",
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum of the level-0 colour launches of one sweep "
+                       "(ncu --set full, cold cache)"}, open(f"{DST}/traffic.json", "w"), indent=1)
 for f in (f"bench_{tag}.json", f"timeline_{tag}.txt"):
     if os.path.exists(f"{OUT}/{f}"):
         open(f"{DST}/{tag}_{f.split('_')[0]}" + os.path.splitext(f)[1], "w").write(open(f"{OUT}/{f}").read())

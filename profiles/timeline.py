@@ -23,7 +23,7 @@ prev_end = 0.0
 per = collections.OrderedDict()
 for name, t0, t1 in ev:
     print(f"{t0:9.2f} {t1:9.2f}  dur {t1 - t0:7.2f}  gap {t0 - prev_end:6.2f}  {name}")
-    key = name.split(" g")[0]
+    key = name.rsplit(" g", 1)[0]
     per.setdefault(key, [0, 0.0])
     per[key][0] += 1
     per[key][1] += t1 - max(t0, prev_end)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "smg_get_phases": (C.c_int, [_vp, C.c_int, _ip, _ip]),
     "smg_level_padded_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_level_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "smg_level_dep_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _ip]),
     "smg_trace_iteration": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip]),
     "smg_launch_count": (C.c_int64, [_vp]),

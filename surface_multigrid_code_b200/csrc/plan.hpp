@@ -52,6 +52,7 @@ std::vector<int> bfs_order(const Csc& A);
 
 // ---- SELL-32 layout ----------------------------------------------------------
 constexpr int kSliceRows = 32;
+constexpr int kBlockRows = 256;  // rows per CTA of the hot kernels
 struct Sell {
   int nrows = 0;                // rows (permuted numbering)
   int nslices = 0;
@@ -99,6 +100,12 @@ struct LevelPlan {
   std::vector<int> phase;     // per row (reference numbering)
   RowOrder order;
   Sell sellA;
+  // Dataflow smoother schedule (multicolour mode): phase p is processed in blocks of
+  // kBlockRows rows starting at (phase_ptr[p] & ~31).  Block b of phase p reads rows of
+  // the blocks [dep_lo, dep_hi] of every other phase q:
+  //   dep[(blk_ofs[p] + b) * n_phases + q] = {lo, hi}  (lo > hi: none)
+  std::vector<int> blk_ofs;           // n_phases + 1
+  std::vector<int> dep_lo, dep_hi;    // n_blocks * n_phases
   // lv >= 1 (operators between level lv-1 (fine) and lv (coarse)):
   Csc P, PT;                  // with values, as the reference leaves mg[lv].P / .PT
   bool pruned = false;

@@ -1296,6 +1296,30 @@ int smg_level_stats(const smg_handle* h, int lv, int64_t* out) {
   return SMG_OK;
 }
 
+int smg_level_dep_stats(const smg_handle* h, int lv, int64_t* out) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !out) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  const int np = L.n_phases;
+  const int64_t nblk = L.blk_ofs.empty() ? 0 : L.blk_ofs.back();
+  int64_t tot = 0, mx = 0;
+  if (!L.dep_lo.empty())
+    for (int64_t b = 0; b < nblk; b++) {
+      int64_t c = 0;
+      for (int q = 0; q < np; q++) {
+        const int lo = L.dep_lo[b * np + q], hi = L.dep_hi[b * np + q];
+        if (hi >= lo) c += hi - lo + 1;
+      }
+      tot += c;
+      mx = std::max(mx, c);
+    }
+  out[0] = nblk;
+  out[1] = tot;
+  out[2] = mx;
+  out[3] = 0;
+  return SMG_OK;
+}
+
 // ---- measurement -----------------------------------------------------------------
 int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush_l2,
                     float* ms_per_rep, int* launches_per_rep) {

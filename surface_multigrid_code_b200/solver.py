@@ -320,6 +320,11 @@ class Solver:
         keys = ("rows", "nnz_ref", "nnz", "padded", "p_nnz", "p_padded", "pt_padded", "phases")
         return dict(zip(keys, [int(v) for v in out]))
 
+    def dep_stats(self, lv) -> dict:
+        out = (C.c_int64 * 4)()
+        self._check(self._lib.smg_level_dep_stats(self._h, lv, out))
+        return dict(zip(("blocks", "dep_total", "dep_max", "dataflow"), [int(v) for v in out]))
+
     # -- measurement --------------------------------------------------------------------------
     def time_kernel(self, which: str, lv: int = 0, k: int = 1, reps: int = 20, flush_l2: bool = False):
         """-> (mean ms per rep, kernel launches per rep); CUDA events on the handle's stream."""
