@@ -46,7 +46,8 @@ typedef enum smg_status {
   SMG_E_CUSOLVER = 6,      /* coarse factorisation failed (matrix not SPD?) */
   SMG_E_NCCL = 7,
   SMG_E_NOT_SYMMETRIC = 8, /* sparsity pattern of A is not symmetric */
-  SMG_E_UNSUPPORTED = 9
+  SMG_E_UNSUPPORTED = 9,
+  SMG_E_INTERNAL = 10      /* a device-side wait timed out (dataflow smoother); results are invalid */
 } smg_status;
 
 typedef enum smg_smoother {
@@ -74,7 +75,12 @@ typedef struct smg_options {
                      dependent step.  Default 0 = off: on B200 a cluster step that exchanges
                      data through L2 costs ~4 us against ~2.2 us for a PDL-chained kernel
                      (profiles/ubench/cluster_step.cu); kept as an experiment */
-  int reserved[7];
+  int dataflow;   /* 1: multicolour phases of one relax call synchronise through per-block epoch
+                     flags instead of waiting for the whole previous phase.  Default 0 = off:
+                     measured slower on B200 (a flag hand-off through L2 costs ~3 us against
+                     ~2.2 us for a PDL kernel boundary, and the CTAs of a phase all finish
+                     together, so there is no wavefront to overlap); kept as an experiment */
+  int reserved[6];
 } smg_options;
 
 void smg_default_options(smg_options *opt);

@@ -30,6 +30,7 @@ STATUS = {
     7: "SMG_E_NCCL",
     8: "SMG_E_NOT_SYMMETRIC",
     9: "SMG_E_UNSUPPORTED",
+    10: "SMG_E_INTERNAL",
 }
 
 SMOOTHER_WAVEFRONT = 0
@@ -60,7 +61,8 @@ class smg_options(C.Structure):
         ("locality_reorder", C.c_int),
         ("sigma", C.c_int),
         ("tail_rows", C.c_int),
-        ("reserved", C.c_int * 7),
+        ("dataflow", C.c_int),
+        ("reserved", C.c_int * 6),
     ]
 
 

@@ -55,6 +55,8 @@ __device__ __forceinline__ double ld_vec(const double* p) {  // mutable vector d
 
 bool g_use_pdl = true;
 bool g_use_tma = true;
+int g_gs_rows = 2;  // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2, 4)
+bool g_gs_attr_set = false;
 
 // ---- optional in-kernel timeline (smg_trace_*): every CTA folds %globaltimer at its
 // start / end into [min start, max end] of the launch's slot.  slot < 0: off.
@@ -236,7 +238,7 @@ __device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const
   }
 }
 
-enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3 };
+enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3, MODE_NORM = 4 };
 
 // y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
 template <int K, int MODE, bool STAGED>
@@ -283,8 +285,8 @@ template <int K, int MODE, int R, int W>
 __global__ void __launch_bounds__(kBlock)
 sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
                         const int* __restrict__ slice_ptr, const int* __restrict__ col,
-                        const double* __restrict__ val, const double* x, int ldx, double* y,
-                        int ldy, double* z) {
+                        const double* __restrict__ val, const double* x, int ldx, const double* b,
+                        double* y, int ldy, double* z) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
@@ -321,22 +323,23 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
   __syncthreads();
   pdl_wait();
   mbar_wait(&bar, 0);
-  double xv[R][W][K], vv[R][W], yv[R][K];
+  double xv[R][W][K], yv[R][K];
 #pragma unroll
   for (int r = 0; r < R; r++) {
 #pragma unroll
     for (int j = 0; j < W; j++)
       if (j < w[r]) {
         const int c = scol[off[r] + j * 32];
-        vv[r][j] = sval[off[r] + j * 32];
 #pragma unroll
         for (int q = 0; q < K; q++) xv[r][j][q] = ld_vec(x + c + (size_t)q * ldx);
       }
-    if (MODE == MODE_ADD && row0 + r * kBlock < nrows) {
+    if ((MODE == MODE_ADD || MODE == MODE_RESIDUAL || MODE == MODE_NORM) && row0 + r * kBlock < nrows) {
+      const double* src = MODE == MODE_ADD ? y : b;
 #pragma unroll
-      for (int q = 0; q < K; q++) yv[r][q] = ld_vec(y + row0 + r * kBlock + (size_t)q * ldy);
+      for (int q = 0; q < K; q++) yv[r][q] = ld_vec(src + row0 + r * kBlock + (size_t)q * ldy);
     }
   }
+  double d2 = 0.0;
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int row = row0 + r * kBlock;
@@ -346,14 +349,32 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
       double sum = 0.0;
 #pragma unroll
       for (int j = 0; j < W; j++)
-        if (j < w[r]) sum = __dadd_rn(sum, __dmul_rn(vv[r][j], xv[r][j][q]));
+        if (j < w[r]) sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], xv[r][j][q]));
       const size_t o = row + (size_t)q * ldy;
       if (MODE == MODE_SPMV) y[o] = sum;
       if (MODE == MODE_ADD) y[o] = __dadd_rn(yv[r][q], sum);
+      if (MODE == MODE_RESIDUAL) y[o] = __dsub_rn(yv[r][q], sum);
+      if (MODE == MODE_NORM) {
+        const double d = __dsub_rn(yv[r][q], sum);
+        d2 += d * d;
+      }
       if (MODE == MODE_SPMV_ZERO) {
         y[o] = sum;
         z[o] = 0.0;
       }
+    }
+  }
+  if (MODE == MODE_NORM) {  // y = per-CTA partial sums; fixed-shape reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
+    __shared__ double wsum[kBlock / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
+      y[blockIdx.x] = t;
     }
   }
   trace_end(trace_slot);
@@ -419,25 +440,184 @@ reduce_partials_kernel(int trace_slot, const double* partial, int n, double* __r
   trace_end(trace_slot);
 }
 
+// Gauss-Seidel phase with R rows per thread (rows 256 apart inside the CTA's R*8 slices,
+// staged by one TMA bulk copy pair): R times fewer, fatter CTAs.  A phase of a large
+// level is bound by CTA turnover (launch + set-up + one DRAM round trip per CTA), not by
+// bandwidth; this amortises it.  Phase-barrier synchronisation only; every slice must be
+// at most kPre wide.
+template <int K, int R>
+__global__ void __launch_bounds__(kBlock)
+sell_gs_phase_multi_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int max_chunk,
+                           const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                           const double* __restrict__ val, const double* __restrict__ diag,
+                           const double* b, double* u, int ld, int pf_slice0, int pf_slice_end) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  const int slice0 = (row0 >> 5) + blockIdx.x * (kSlices * R);
+  const int rbase = row0 + blockIdx.x * (kBlock * R) + threadIdx.x;
+  double* sval = reinterpret_cast<double*>(dyn);
+  int* scol = reinterpret_cast<int*>(dyn + (size_t)max_chunk * sizeof(double));
+  const int e0 = slice_ptr[slice0 < nslices ? slice0 : nslices];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    const int s1 = slice0 + kSlices * R < nslices ? slice0 + kSlices * R : nslices;
+    const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - e0);
+    const uint64_t pol = l2_evict_first_policy();
+    mbar_expect_tx(&bar, nent * 12u);
+    if (nent > 0) {
+      bulk_g2s(sval, val + e0, nent * 8u, &bar, pol);
+      bulk_g2s(scol, col + e0, nent * 4u, &bar, pol);
+    }
+  }
+  if (pf_slice0 >= 0 && threadIdx.x == 32) {  // next phase's chunk -> L2 (see the R = 1 kernel)
+    const int s0 = pf_slice0 + blockIdx.x * (kSlices * R);
+    if (s0 < pf_slice_end) {
+      const int s1 = s0 + kSlices * R < pf_slice_end ? s0 + kSlices * R : pf_slice_end;
+      const int p0 = slice_ptr[s0];
+      const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - p0);
+      if (nent > 0) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(val + p0), "r"(nent * 8u) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(col + p0), "r"(nent * 4u) : "memory");
+      }
+    }
+  }
+  int off[R], w[R];
+  double d[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row = rbase + r * kBlock;
+    w[r] = 0;
+    off[r] = 0;
+    d[r] = 1.0;
+    if (row >= ps && row < pe) {
+      const int s = row >> 5;
+      const int base = slice_ptr[s];
+      w[r] = (slice_ptr[s + 1] - base) >> 5;
+      off[r] = base - e0 + (row & 31);
+      d[r] = ld_stream_f64(diag + row);
+    }
+  }
+  __syncthreads();
+  pdl_wait();
+  mbar_wait(&bar, 0);
+  double xv[R][kPre][K], bv[R][K];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row = rbase + r * kBlock;
+#pragma unroll
+    for (int j = 0; j < kPre; j++)
+      if (j < w[r]) {
+        const int c = scol[off[r] + j * 32];
+        if (c != row) {
+#pragma unroll
+          for (int q = 0; q < K; q++) xv[r][j][q] = ld_vec(u + c + (size_t)q * ld);
+        }
+      }
+    if (w[r] > 0) {
+#pragma unroll
+      for (int q = 0; q < K; q++) bv[r][q] = ld_vec(b + row + (size_t)q * ld);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row = rbase + r * kBlock;
+    if (w[r] == 0) continue;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < kPre; j++)
+        if (j < w[r] && scol[off[r] + j * 32] != row)
+          sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], xv[r][j][q]));
+      u[row + (size_t)q * ld] = __ddiv_rn(__dsub_rn(bv[r][q], sum), d[r]);
+    }
+  }
+  trace_end(trace_slot);
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
 // independent, so updating them in place and in parallel is exactly the sequential
-// sweep of mg_VCycle.cpp:147-158 restricted to those rows.
+// sweep of mg_VCycle.cpp:147-158 restricted to those rows.  Synchronisation with the
+// other phases: see GsFlow (kernels.hpp).
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int max_chunk,
                      const int* __restrict__ slice_ptr, const int* __restrict__ col,
                      const double* __restrict__ val, const double* __restrict__ diag,
-                     const double* b, double* u, int ld) {
+                     const double* b, double* u, int ld, const GsFlow flow) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
-  pdl_launch_dependents();
+  const bool dataflow = flow.mode == 1;
+  // Dataflow: the first launch of a relax call releases its dependents only AFTER its own
+  // PDL wait, so no later launch of the call can run before everything that precedes the
+  // call has completed (and the epoch base in ctrl[0] is final).
+  if (!(dataflow && flow.first)) pdl_launch_dependents();
   const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
   const bool active = row >= ps && row < pe;
   const RowView rv = stage_rows<STAGED>((row0 >> 5) + blockIdx.x * kSlices, nslices, row, active,
                                         slice_ptr, col, val, max_chunk, dyn, &bar);
   const double d = active ? ld_stream_f64(diag + row) : 1.0;
-  pdl_wait();
+  // While this phase gathers, stores and drains, DRAM would idle: ask for the matrix chunk
+  // that the same CTA index of the NEXT phase will stream, so that its TMA hits L2.
+  if (flow.pf_slice0 >= 0 && threadIdx.x == 32) {
+    const int s0 = flow.pf_slice0 + blockIdx.x * kSlices;
+    if (s0 < flow.pf_slice_end) {
+      const int s1 = s0 + kSlices < flow.pf_slice_end ? s0 + kSlices : flow.pf_slice_end;
+      const int e0 = slice_ptr[s0];
+      const uint32_t nent = static_cast<uint32_t>(slice_ptr[s1] - e0);
+      if (nent > 0) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(val + e0), "r"(nent * 8u) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(col + e0), "r"(nent * 4u) : "memory");
+      }
+    }
+  }
+  int epoch = 0;
+  if (!dataflow) {
+    pdl_wait();
+  } else {
+    if (flow.first) {
+      pdl_wait();
+      pdl_launch_dependents();
+    }
+    const int base = ld_acquire_gpu(flow.ctrl);
+    const int t = flow.it * flow.np + flow.p;
+    epoch = base + t + 1;
+    if (threadIdx.x < 32) {
+      // wait for the blocks this block reads from / whose readers it overwrites: the most
+      // recent launch of every other phase q (same sweep if q < p, previous sweep otherwise)
+      const int2* dep = flow.dep + (static_cast<size_t>(flow.blk_ofs[flow.p]) + blockIdx.x) * flow.np;
+      for (int q = 0; q < flow.np; q++) {
+        if (q == flow.p) continue;
+        const int tq = (q < flow.p ? flow.it : flow.it - 1) * flow.np + q;
+        if (tq < 0) continue;  // before this call: complete, see above
+        const int need = base + tq + 1;
+        const int2 r = dep[q];
+        const int* fq = flow.flags + flow.blk_ofs[q];
+        for (int j = r.x + (int)threadIdx.x; j <= r.y; j += 32) {
+          int spins = 0;
+          while (ld_acquire_gpu(fq + j) - need < 0) {
+            if (++spins > (1 << 24)) {  // never hang the GPU: flag the error and go on
+              atomicExch(flow.ctrl + 2, 1);
+              break;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
   stage_wait<STAGED>(&bar);
   if (active) {
     double sum[K];
@@ -448,6 +628,42 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
     for (int q = 0; q < K; q++) {
       const size_t o = row + (size_t)q * ld;
       u[o] = __ddiv_rn(__dsub_rn(ld_vec(b + o), sum[q]), d);
+    }
+  }
+  if (dataflow) {
+    __syncthreads();  // every row of the block is written
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_gpu(flow.flags + flow.blk_ofs[flow.p] + blockIdx.x, epoch);
+    }
+    // The middle launches of a call never execute a PDL wait, so their formal completion
+    // is not ordered with anything.  Instead the LAST launch does not complete before every
+    // block of every phase has published its final epoch of this call: "last launch
+    // complete" (what the next kernel's PDL wait sees) then implies "call complete", and
+    // all of the call's writes are visible through the release/acquire chain.
+    if (flow.last) {
+      const int base = epoch - (flow.it * flow.np + flow.p + 1);
+      const int nblk = flow.blk_ofs[flow.np];
+      for (int j = blockIdx.x * kBlock + threadIdx.x; j < nblk; j += gridDim.x * kBlock) {
+        int q = 0;
+        while (q + 1 < flow.np && flow.blk_ofs[q + 1] <= j) q++;
+        const int need = base + (flow.iters - 1) * flow.np + q + 1;
+        int spins = 0;
+        while (ld_acquire_gpu(flow.flags + j) - need < 0) {
+          if (++spins > (1 << 24)) {
+            atomicExch(flow.ctrl + 2, 1);
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(flow.ctrl + 1, 1) == (int)gridDim.x - 1) {  // last block of the call
+          atomicExch(flow.ctrl + 1, 0);
+          atomicAdd(flow.ctrl, flow.iters * flow.np);  // epoch base of the next call
+        }
+      }
     }
   }
   trace_end(trace_slot);
@@ -628,6 +844,19 @@ void trace_label(const char* label) { g_trace.label = label; }
 int trace_count() { return g_trace.next; }
 const char* trace_name(int i) { return g_trace.names[i].c_str(); }
 void set_tma_enabled(bool on) { g_use_tma = on; }
+void set_gs_rows(int r) {
+  g_gs_rows = r >= 4 ? 4 : (r >= 2 ? 2 : 1);
+  g_gs_attr_set = true;
+  // more than 48 KB of dynamic shared memory needs an opt-in
+  cudaFuncSetAttribute(sell_gs_phase_multi_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(sell_gs_phase_multi_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int big = 100 * 1024;
+  cudaFuncSetAttribute(sell_apply_short_kernel<1, MODE_SPMV, 2, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_short_kernel<1, MODE_RESIDUAL, 2, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_short_kernel<1, MODE_ADD, 2, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_short_kernel<1, MODE_SPMV_ZERO, 2, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_short_kernel<1, MODE_NORM, 2, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+}
 
 #define SMG_DISPATCH_K(k, ...)                 \
   switch (k) {                                 \
@@ -638,7 +867,7 @@ void set_tma_enabled(bool on) { g_use_tma = on; }
   }
 
 namespace {
-const char* const kApplyNames[4] = {"spmv", "residual", "prolong_add", "restrict_zero"};
+const char* const kApplyNames[5] = {"spmv", "residual", "prolong_add", "restrict_zero", "residual_norm"};
 inline size_t stage_bytes(const SellDev& M) { return static_cast<size_t>(M.max_chunk) * 12; }
 inline bool use_staged(const SellDev& M) {
   return g_use_tma && M.max_chunk > 0 && stage_bytes(M) <= static_cast<size_t>(kStageCapBytes);
@@ -649,13 +878,21 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
                   double* y, int ldy, double* z, int k, cudaStream_t st) {
   if (M.nrows <= 0) return;
   constexpr int R = 4, W = 3;
-  if (MODE != MODE_RESIDUAL && g_use_tma && M.max_width <= W && M.max_chunk32 > 0 &&
+  if (g_use_tma && M.max_width <= W && M.max_chunk32 > 0 &&
       static_cast<size_t>(M.max_chunk32) * 12 <= static_cast<size_t>(kStageCapBytes)) {
     const int gs = blocks_for(M.nrows, kBlock * R);
-    constexpr int SM = MODE == MODE_RESIDUAL ? MODE_SPMV : MODE;  // (never instantiated for residual)
-    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<K, SM, R, W>, gs, kBlock,
+    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<K, MODE, R, W>, gs, kBlock,
                                     static_cast<size_t>(M.max_chunk32) * 12, st, M.nrows, M.nslices,
-                                    M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, y, ldy, z));
+                                    M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z));
+    return;
+  }
+  // large levels, k = 1: two rows per thread (fewer, fatter CTAs; see the Gauss-Seidel kernel)
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && M.nrows >= 600000 &&
+      M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
+    if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
+    launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(M.nrows, kBlock * 2),
+                  kBlock, static_cast<size_t>(M.max_chunk16) * 12, st, M.nrows, M.nslices, M.max_chunk16,
+                  M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z);
     return;
   }
   const int g = blocks_for(M.nrows, kBlock);
@@ -695,7 +932,17 @@ int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, k
 
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st) {
-  const int g = residual_norm_blocks(M.nrows);
+  int g = residual_norm_blocks(M.nrows);
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && M.nrows >= 600000 &&
+      M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
+    if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
+    g = blocks_for(M.nrows, kBlock * 2);
+    launch_kernel("residual_norm", sell_apply_short_kernel<1, MODE_NORM, 2, kPre>, g, kBlock,
+                  static_cast<size_t>(M.max_chunk16) * 12, st, M.nrows, M.nslices, M.max_chunk16,
+                  M.slice_ptr, M.col, M.valT, x, ld, b, scratch, ld, nullptr);
+    launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
+    return;
+  }
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
                                     st, M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
@@ -709,18 +956,37 @@ void launch_residual_norm2(const SellDev& M, const double* b, const double* x, i
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
-                     int k, int ps, int pe, cudaStream_t st) {
+                     int k, int ps, int pe, const GsFlow& flow, cudaStream_t st) {
   if (pe <= ps) return;
   const int row0 = ps & ~31;
+  // large phases: R rows per thread (fewer, fatter CTAs)
+  if (g_gs_rows > 1 && flow.mode == 0 && g_use_tma && k == 1 && M.max_width <= kPre &&
+      pe - row0 >= 150000) {  // at least one full wave of fat CTAs
+    if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
+    const int R = g_gs_rows;
+    const int mc = R == 2 ? M.max_chunk16 : M.max_chunk32s;
+    if (mc > 0 && static_cast<size_t>(mc) * 12 <= 100 * 1024) {
+      const int gr = blocks_for(pe - row0, kBlock * R);
+      if (R == 2)
+        launch_kernel("gs_phase", sell_gs_phase_multi_kernel<1, 2>, gr, kBlock, static_cast<size_t>(mc) * 12, st,
+                      row0, ps, pe, M.nslices, mc, M.slice_ptr, M.col, M.val, diag, b, u, ld,
+                      flow.pf_slice0, flow.pf_slice_end);
+      else
+        launch_kernel("gs_phase", sell_gs_phase_multi_kernel<1, 4>, gr, kBlock, static_cast<size_t>(mc) * 12, st,
+                      row0, ps, pe, M.nslices, mc, M.slice_ptr, M.col, M.val, diag, b, u, ld,
+                      flow.pf_slice0, flow.pf_slice_end);
+      return;
+    }
+  }
   const int g = blocks_for(pe - row0, kBlock);
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel("gs_phase", sell_gs_phase_kernel<K, true>, g, kBlock, stage_bytes(M), st,
                                     row0, ps, pe, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val,
-                                    diag, b, u, ld));
+                                    diag, b, u, ld, flow));
   } else {
     SMG_DISPATCH_K(k, launch_kernel("gs_phase", sell_gs_phase_kernel<K, false>, g, kBlock, 0, st, row0, ps, pe,
                                     M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val, diag, b, u,
-                                    ld));
+                                    ld, flow));
   }
 }
 

@@ -16,6 +16,7 @@ struct SellDev {
   int max_chunk = 0;  // most stored entries in any 8 consecutive slices (one CTA's chunk)
   int max_width = 0;  // widest slice (entries per row)
   int max_chunk32 = 0;  // most stored entries in any aligned group of 32 slices
+  int max_chunk16 = 0, max_chunk32s = 0;  // ... in any 16 / 32 consecutive slices
   const int* slice_ptr = nullptr;
   const int* col = nullptr;
   const double* val = nullptr;
@@ -34,6 +35,8 @@ void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, dou
 void set_pdl_enabled(bool on);
 // TMA (cp.async.bulk) staging of the matrix chunks in shared memory (default on)
 void set_tma_enabled(bool on);
+// rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2 or 4)
+void set_gs_rows(int r);
 // ---- cluster "tail" kernel ---------------------------------------------------------
 // Levels too small to fill the GPU are latency-bound: a chain of per-phase kernels
 // costs ~2 us per dependent step.  The tail kernel runs a whole list of such steps
@@ -77,9 +80,29 @@ void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, i
 int residual_norm_blocks(int nrows);
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st);
+// Dataflow schedule of the smoother.  mode 0: every phase kernel waits (PDL) for the whole
+// previous phase.  mode 1: only the first phase kernel of a relax call waits for its
+// predecessor; inside the call a 256-row block waits just for the blocks of the other
+// phases whose rows it reads (or whose readers it would overwrite), through per-block
+// epoch flags in global memory, so consecutive phases overlap like a wavefront instead of
+// draining the GPU at every colour change.
+struct GsFlow {
+  int mode = 0;
+  int np = 0;               // phases per sweep
+  int p = 0, it = 0;        // this launch: phase p of sweep it
+  int iters = 0;            // sweeps of this relax call
+  int first = 0, last = 0;  // first / last (non-empty) launch of the call
+  const int2* dep = nullptr;     // [(blk_ofs[p] + b) * np + q] = {lo, hi} blocks of phase q
+  const int* blk_ofs = nullptr;  // np + 1
+  int* flags = nullptr;          // epoch per block
+  int* ctrl = nullptr;           // [0] epoch base, [1] finished blocks of the last launch, [2] error
+  // L2 prefetch of the NEXT launch's matrix chunk (both modes): CTA b asks for the slices
+  // [pf_slice0 + 8 b, pf_slice0 + 8 b + 8) clipped to pf_slice_end; pf_slice0 < 0: none
+  int pf_slice0 = -1, pf_slice_end = 0;
+};
 // one Gauss-Seidel phase: rows [ps, pe) of the permuted matrix, in place on u
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
-                     int k, int ps, int pe, cudaStream_t st);
+                     int k, int ps, int pe, const GsFlow& flow, cudaStream_t st);
 
 // ---- setup-time numeric kernels ---------------------------------------------
 // out[i] = in[idx[i]]

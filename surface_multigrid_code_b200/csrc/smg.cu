@@ -89,7 +89,8 @@ struct DevBuf {
 struct SellBufs {
   DevBuf<int> slice_ptr, col, src;
   DevBuf<double> val, valT;
-  int nrows = 0, nslices = 0, max_chunk = 0, max_width = 0, max_chunk32 = 0;
+  int nrows = 0, nslices = 0, max_chunk = 0, max_width = 0, max_chunk32 = 0, max_chunk16 = 0,
+      max_chunk32s = 0;
   int64_t padded = 0;
   SellDev view() const {
     SellDev d;
@@ -98,6 +99,8 @@ struct SellBufs {
     d.max_chunk = max_chunk;
     d.max_width = max_width;
     d.max_chunk32 = max_chunk32;
+    d.max_chunk16 = max_chunk16;
+    d.max_chunk32s = max_chunk32s;
     d.slice_ptr = slice_ptr.p;
     d.col = col.p;
     d.val = val.p;
@@ -115,6 +118,10 @@ struct LevelDev {
   DevBuf<double> diag;  // permuted numbering
   DevBuf<int> perm;     // new -> old
   std::vector<int> phase_ptr;
+  // dataflow smoother (kernels.hpp::GsFlow)
+  bool dataflow = false;
+  DevBuf<int2> dep;
+  DevBuf<int> blk_ofs, flags, ctrl;
   // transfer operators between level l-1 (fine) and l (coarse), l >= 1
   SellBufs sellP, sellPT;
   DevBuf<int> p_colptr, p_rowidx, pt_colptr, pt_rowidx;  // CSC of P and of PT
@@ -320,11 +327,13 @@ int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT
   out->nrows = S.nrows;
   out->nslices = S.nslices;
   out->padded = S.padded();
-  out->max_chunk = out->max_width = out->max_chunk32 = 0;
+  out->max_chunk = out->max_width = out->max_chunk32 = out->max_chunk16 = out->max_chunk32s = 0;
   for (int s0 = 0; s0 < S.nslices; s0++) {  // any 8 consecutive slices: one CTA's TMA chunk
     const int s1 = std::min(S.nslices, s0 + 8);
     out->max_chunk = std::max(out->max_chunk, S.slice_ptr[s1] - S.slice_ptr[s0]);
     out->max_width = std::max(out->max_width, (S.slice_ptr[s0 + 1] - S.slice_ptr[s0]) / 32);
+    out->max_chunk16 = std::max(out->max_chunk16, S.slice_ptr[std::min(S.nslices, s0 + 16)] - S.slice_ptr[s0]);
+    out->max_chunk32s = std::max(out->max_chunk32s, S.slice_ptr[std::min(S.nslices, s0 + 32)] - S.slice_ptr[s0]);
     if (s0 % 32 == 0)
       out->max_chunk32 = std::max(out->max_chunk32,
                                   S.slice_ptr[std::min(S.nslices, s0 + 32)] - S.slice_ptr[s0]);
@@ -357,15 +366,46 @@ void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, i
   LevelDev& L = h->lv[l];
   const SellDev A = L.sellA.view();
   const int np = static_cast<int>(L.phase_ptr.size()) - 1;
-  for (int it = 0; it < iters; it++)
-    for (int p = 0; p < np; p++)
-      for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
-        const int kk = std::min(smg::kMaxK, k - k0);
+  int p_first = -1, p_last = -1;  // non-empty phases
+  for (int p = 0; p < np; p++)
+    if (L.phase_ptr[p + 1] > L.phase_ptr[p]) {
+      if (p_first < 0) p_first = p;
+      p_last = p;
+    }
+  if (p_first < 0 || iters <= 0) return;
+  smg::GsFlow flow;
+  flow.mode = L.dataflow && (p_last > p_first || iters > 1) ? 1 : 0;
+  flow.np = np;
+  flow.iters = iters;
+  flow.dep = L.dep.p;
+  flow.blk_ofs = L.blk_ofs.p;
+  flow.flags = L.flags.p;
+  flow.ctrl = L.ctrl.p;
+  // the columns of a block of right-hand sides are independent: one complete relax call
+  // (its own epoch range) per group of kMaxK columns
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    for (int it = 0; it < iters; it++)
+      for (int p = 0; p < np; p++) {
+        if (L.phase_ptr[p + 1] <= L.phase_ptr[p]) continue;
+        flow.p = p;
+        flow.it = it;
+        flow.first = it == 0 && p == p_first;
+        flow.last = it == iters - 1 && p == p_last;
+        // next non-empty phase of this call (its matrix chunk is prefetched into L2)
+        flow.pf_slice0 = -1;
+        if (!flow.last && h->opt.reserved[0] == 0) {
+          int q = p;
+          do q = (q + 1) % np; while (L.phase_ptr[q + 1] <= L.phase_ptr[q]);
+          flow.pf_slice0 = L.phase_ptr[q] >> 5;
+          flow.pf_slice_end = (L.phase_ptr[q + 1] + 31) >> 5;
+        }
         smg::launch_gs_phase(A, L.diag.p, b + static_cast<size_t>(k0) * L.n,
                              u + static_cast<size_t>(k0) * L.n, L.n, kk, L.phase_ptr[p],
-                             L.phase_ptr[p + 1], h->stream);
-        if (L.phase_ptr[p + 1] > L.phase_ptr[p]) h->launches++;
+                             L.phase_ptr[p + 1], flow, h->stream);
+        h->launches++;
       }
+  }
 }
 
 void residual_device(smg_handle* h, int l, const double* b, const double* u, double* r, int k) {
@@ -636,6 +676,17 @@ int upload_plan(smg_handle* h) {
     SMG_CUDA(h, L.diag.alloc(static_cast<size_t>(P.n)));
     SMG_CUDA(h, L.perm.upload(P.order.perm, st));
     L.phase_ptr = P.order.phase_ptr;
+    L.dataflow = h->opt.dataflow && h->opt.smoother == SMG_SMOOTHER_MULTICOLOUR && P.n_phases >= 2 &&
+                 !P.dep_lo.empty();
+    if (L.dataflow) {
+      std::vector<int2> dep(P.dep_lo.size());
+      for (size_t i = 0; i < dep.size(); i++) dep[i] = make_int2(P.dep_lo[i], P.dep_hi[i]);
+      SMG_CUDA(h, L.dep.upload(dep, st));
+      SMG_CUDA(h, L.blk_ofs.upload(P.blk_ofs, st));
+      SMG_CUDA(h, L.flags.upload(std::vector<int>(static_cast<size_t>(P.blk_ofs.back()), 0), st));
+      SMG_CUDA(h, L.ctrl.upload(std::vector<int>(4, 0), st));
+      SMG_CUDA(h, cudaStreamSynchronize(st));  // the temporaries above go out of scope
+    }
     if (l >= 1) {
       SMG_TRY(upload_sell(h, P.sellP, &L.sellP, false));
       SMG_TRY(upload_sell(h, P.sellPT, &L.sellPT, false));
@@ -767,6 +818,24 @@ int valid_level(smg_handle* h, int lv, bool need_coarser) {
   return SMG_OK;
 }
 
+// a dataflow wait that timed out leaves ctrl[2] != 0 on its level
+int check_dataflow(smg_handle* h) {
+  int* flags = reinterpret_cast<int*>(h->h_norm + 32);  // pinned scratch
+  int n = 0;
+  for (auto& L : h->lv)
+    if (L.dataflow && n < 32) {
+      flags[n] = 0;
+      SMG_CUDA(h, cudaMemcpyAsync(flags + n, L.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      n++;
+    }
+  if (n == 0) return SMG_OK;
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  int bad = 0;
+  for (int i = 0; i < n; i++) bad |= flags[i];
+  if (bad) return fail(h, SMG_E_INTERNAL, "dataflow smoother: a device-side wait timed out");
+  return SMG_OK;
+}
+
 // min_quad_with_fixed_mg_solve on device pointers
 int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const double* d_z0, int k,
                double tol, int max_iter, double* d_z, double* r_his, int* n_his, int* converged) {
@@ -806,6 +875,7 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
     h->launches++;
   }
   SMG_TRY(check_launch(h, "solve"));
+  SMG_TRY(check_dataflow(h));
   *n_his = nh;
   *converged = residual > tol ? 0 : 1;  // cpp:357-360 (stale residual, by design)
   return SMG_OK;
@@ -853,6 +923,7 @@ void smg_default_options(smg_options* opt) {
   opt->verbose = 0;
   opt->locality_reorder = 1;
   opt->sigma = 256;
+  opt->dataflow = 0;  // measured slower than phase barriers on B200, see DESIGN.md section 4
   opt->tail_rows = 0;  // measured slower than the PDL kernel chain on B200, see DESIGN.md section 4
 }
 
@@ -870,6 +941,7 @@ const char* smg_status_string(int status) {
     case SMG_E_NCCL: return "NCCL error";
     case SMG_E_NOT_SYMMETRIC: return "matrix pattern is not symmetric";
     case SMG_E_UNSUPPORTED: return "unsupported";
+    case SMG_E_INTERNAL: return "internal error (device-side wait timed out)";
   }
   return "unknown status";
 }
@@ -910,6 +982,9 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   }
   h->device = dev;
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
+  if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
+  if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->opt.reserved[0] = (e[0] && e[0] != '0');
+  if (const char* e = std::getenv("SMG_DATAFLOW")) h->opt.dataflow = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_TAIL_ROWS")) h->opt.tail_rows = std::atoi(e);
   h->tail_cluster = h->opt.tail_rows > 0 ? smg::tail_cluster_size() : 0;
   if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));

@@ -63,7 +63,8 @@ class Solver:
 
     def __init__(self, smoother: str = "multicolour", device=None, use_graph: bool = True,
                  pre_relax: int = 2, post_relax: int = 2, verbose: bool = False,
-                 locality_reorder: bool = True, sigma: int = 256, tail_rows: Optional[int] = None):
+                 locality_reorder: bool = True, sigma: int = 256, tail_rows: Optional[int] = None,
+                 dataflow: Optional[bool] = None):
         self._lib = L.load()
         opt = L.smg_options()
         self._lib.smg_default_options(C.byref(opt))
@@ -83,6 +84,8 @@ class Solver:
         opt.sigma = int(sigma)
         if tail_rows is not None:
             opt.tail_rows = int(tail_rows)
+        if dataflow is not None:
+            opt.dataflow = int(bool(dataflow))
         self.smoother = smoother
         self.plan_only = device == "none"
         self._h = L._vp()
