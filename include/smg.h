@@ -158,6 +158,51 @@ int smg_prolong(smg_handle *h, int lv, const double *x, double *Px, int k);
 /* coarseSolve (src/mg_VCycle.cpp:181-201): u = u + A_coarsest^-1 B */
 int smg_coarse_solve(smg_handle *h, const double *B, double *u, int k);
 
+/* ---- multi-GPU: row-range partition of the fine levels over the ranks of one node ----
+ * The reference is a single-threaded CPU code (no MPI/NCCL anywhere): this block has no
+ * reference counterpart, it is the row-range partition BASELINE.json's north_star asks for.
+ * One process (or thread) per GPU, one handle per rank.  Levels 0 .. dist_levels-1 are
+ * partitioned by rows (strips of a breadth-first order of the level's graph); every rank
+ * runs the smoother / residual / restriction / prolongation of its own rows and exchanges
+ * halo values with the other ranks through peer-mapped device memory (stores over NVLink +
+ * epoch flags, inside the same CUDA graph as the compute kernels; no host round trip, no
+ * NCCL call on the data path).  Coarser levels and the coarse direct solve are replicated.
+ * Call order: smg_create, smg_dist_init, smg_dist_get_handle, [the host all-gathers the
+ * blobs, e.g. torch.distributed.all_gather / MPI_Allgather / a file], smg_dist_connect,
+ * then smg_set_hierarchy / smg_precompute / smg_solve as usual.  Every compute entry point
+ * becomes COLLECTIVE: all ranks make the same calls with the same (replicated) arguments and
+ * all ranks receive the complete result.  Synchronise the ranks (host barrier) before
+ * smg_destroy. */
+/* comm_bytes: size of the peer-mapped staging buffer (0 = 256 MiB).  Plan-only handles
+ * accept the call and partition the plan without allocating anything. */
+int smg_dist_init(smg_handle *h, int rank, int world, size_t comm_bytes);
+int smg_dist_handle_bytes(void);
+/* this rank's export blob (smg_dist_handle_bytes() bytes): CUDA IPC handle + pid */
+int smg_dist_get_handle(smg_handle *h, void *blob);
+/* all_blobs: world blobs in rank order.  Buffers of ranks living in the same process are
+ * used directly (peer access), others are opened with cudaIpcOpenMemHandle. */
+int smg_dist_connect(smg_handle *h, const void *all_blobs);
+/* exact = 1: halo exchange after every colour (the N-rank smoother is then the same
+ * multicolour Gauss-Seidel as on one GPU); 0 (default): one exchange per sweep (Gauss-Seidel
+ * inside a rank, Jacobi coupling across ranks).  dist_levels < 0: automatic (levels with at
+ * least dist_min_rows rows per rank, default 100000; always level 0).  Before smg_precompute. */
+int smg_dist_set_options(smg_handle *h, int exact, int dist_levels, int dist_min_rows);
+/* out[8]: [0] rank [1] world [2] partitioned levels [3] halo exchanges issued so far
+ * [4] connected [5] staging doubles per (peer, parity) slot */
+int smg_dist_info(const smg_handle *h, int64_t *out);
+/* out[8] for level lv: [0] layout (0 plain, 1 partitioned, 2 split) [1] parts
+ * [2] rows owned by this rank [3] halo rows of u this rank receives per exchange
+ * [4] halo rows it sends [5] halo rows of r received [6] first owned row [7] end */
+int smg_dist_level_info(const smg_handle *h, int lv, int64_t *out);
+/* owner rank of every row of level lv (reference numbering) */
+int smg_dist_get_part(const smg_handle *h, int lv, int *part_of_row);
+typedef enum smg_exchange_id { SMG_X_HALO_U = 0, SMG_X_HALO_R = 1, SMG_X_HALO_PU = 2,
+                               SMG_X_GATHER = 3 } smg_exchange_id;
+/* rows (reference numbering of level lv) whose values travel src -> dst in exchange
+ * `which`; idx may be NULL to query *n */
+int smg_dist_get_exchange(const smg_handle *h, int lv, int which, int src, int dst, int *idx,
+                          int *n);
+
 /* ---- index / topology outputs (bit-exact parity surface) ------------------ */
 int smg_num_levels(const smg_handle *h);
 int smg_level_rows(const smg_handle *h, int lv); /* rows of mg[lv].A, <0 on error */

@@ -91,6 +91,15 @@ SIGNATURES = {
     "smg_restrict": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "smg_prolong": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),
     "smg_coarse_solve": (C.c_int, [_vp, _dp, _dp, C.c_int]),
+    "smg_dist_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_size_t]),
+    "smg_dist_handle_bytes": (C.c_int, []),
+    "smg_dist_get_handle": (C.c_int, [_vp, _vp]),
+    "smg_dist_connect": (C.c_int, [_vp, _vp]),
+    "smg_dist_set_options": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "smg_dist_info": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "smg_dist_level_info": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "smg_dist_get_part": (C.c_int, [_vp, C.c_int, _ip]),
+    "smg_dist_get_exchange": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip]),
     "smg_num_levels": (C.c_int, [_vp]),
     "smg_level_rows": (C.c_int, [_vp, C.c_int]),
     "smg_num_unknown": (C.c_int, [_vp]),

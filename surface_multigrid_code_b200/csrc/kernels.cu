@@ -14,6 +14,7 @@
 // parity in wavefront mode depends on it.
 #include "kernels.hpp"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,15 @@ __device__ __forceinline__ double ld_vec(const double* p) {  // mutable vector d
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 bool g_use_pdl = true;
@@ -243,16 +253,16 @@ enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3, MODE_
 // y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
 template <int K, int MODE, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_apply_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+sell_apply_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                   const int* __restrict__ col, const double* __restrict__ val, const double* x,
                   int ldx, const double* b, double* y, int ldy, double* z) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
   pdl_launch_dependents();
-  const int row = blockIdx.x * kBlock + threadIdx.x;
-  const bool active = row < nrows;
-  const RowView rv = stage_rows<STAGED>(blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
+  const int row = (rb & ~31) + blockIdx.x * kBlock + threadIdx.x;
+  const bool active = row >= rb && row < re;
+  const RowView rv = stage_rows<STAGED>((rb >> 5) + blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
                                         val, max_chunk, dyn, &bar);
   pdl_wait();
   stage_wait<STAGED>(&bar);
@@ -283,7 +293,7 @@ sell_apply_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const i
 // the first sum.  Requires every slice to be at most W wide.
 template <int K, int MODE, int R, int W>
 __global__ void __launch_bounds__(kBlock)
-sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
+sell_apply_short_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk,
                         const int* __restrict__ slice_ptr, const int* __restrict__ col,
                         const double* __restrict__ val, const double* x, int ldx, const double* b,
                         double* y, int ldy, double* z) {
@@ -291,8 +301,8 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
   pdl_launch_dependents();
-  const int slice0 = blockIdx.x * (kSlices * R);
-  const int row0 = blockIdx.x * (kBlock * R) + threadIdx.x;
+  const int slice0 = (rb >> 5) + blockIdx.x * (kSlices * R);
+  const int row0 = (rb & ~31) + blockIdx.x * (kBlock * R) + threadIdx.x;
   double* sval = reinterpret_cast<double*>(dyn);
   int* scol = reinterpret_cast<int*>(dyn + (size_t)max_chunk * sizeof(double));
   const int e0 = slice_ptr[slice0];
@@ -313,7 +323,7 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
     const int row = row0 + r * kBlock;
     w[r] = 0;
     off[r] = 0;
-    if (row < nrows) {
+    if (row >= rb && row < re) {
       const int s = row >> 5;
       const int base = slice_ptr[s];
       w[r] = (slice_ptr[s + 1] - base) >> 5;
@@ -333,7 +343,8 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
 #pragma unroll
         for (int q = 0; q < K; q++) xv[r][j][q] = ld_vec(x + c + (size_t)q * ldx);
       }
-    if ((MODE == MODE_ADD || MODE == MODE_RESIDUAL || MODE == MODE_NORM) && row0 + r * kBlock < nrows) {
+    if ((MODE == MODE_ADD || MODE == MODE_RESIDUAL || MODE == MODE_NORM) && row0 + r * kBlock >= rb &&
+        row0 + r * kBlock < re) {
       const double* src = MODE == MODE_ADD ? y : b;
 #pragma unroll
       for (int q = 0; q < K; q++) yv[r][q] = ld_vec(src + row0 + r * kBlock + (size_t)q * ldy);
@@ -343,7 +354,7 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int row = row0 + r * kBlock;
-    if (row >= nrows) continue;
+    if (row < rb || row >= re) continue;
 #pragma unroll
     for (int q = 0; q < K; q++) {
       double sum = 0.0;
@@ -382,16 +393,16 @@ sell_apply_short_kernel(int trace_slot, int nrows, int nslices, int max_chunk,
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
-sell_residual_norm_kernel(int trace_slot, int nrows, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+sell_residual_norm_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                           const int* __restrict__ col, const double* __restrict__ val,
                           const double* x, const double* b, int ld, double* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
   pdl_launch_dependents();
-  const int row = blockIdx.x * kBlock + threadIdx.x;
-  const bool active = row < nrows;
-  const RowView rv = stage_rows<STAGED>(blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
+  const int row = (rb & ~31) + blockIdx.x * kBlock + threadIdx.x;
+  const bool active = row >= rb && row < re;
+  const RowView rv = stage_rows<STAGED>((rb >> 5) + blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
                                         val, max_chunk, dyn, &bar);
   pdl_wait();
   stage_wait<STAGED>(&bar);
@@ -537,14 +548,6 @@ sell_gs_phase_multi_kernel(int trace_slot, int row0, int ps, int pe, int nslices
   trace_end(trace_slot);
 }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
 // independent, so updating them in place and in parallel is exactly the sequential
@@ -665,6 +668,93 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
         }
       }
     }
+  }
+  trace_end(trace_slot);
+}
+
+// ---- multi-GPU halo exchange (see kernels.hpp::XchgPeer) --------------------------------
+// Grid (ctas per peer, npeers).  Every CTA: (1) pushes its share of the send list into the
+// peer's staging slot with plain stores over NVLink, (2) the last CTA of a peer group to
+// finish publishes the epoch in the peer's flag (release at system scope), (3) waits for
+// the peer's epoch in its own flag, (4) scatters its share of the received values.
+// No CTA waits before it has pushed, so two ranks can never wait for each other; a wait
+// that exceeds the timeout (a peer died) sets ctrl[2] and falls through instead of hanging
+// the GPU.
+// ctrl layout: [2] error flag, [8 + peer] arrival counter, [8 + 64 + peer] exit counter,
+// [8 + 128 + peer] epoch of the peer group (advanced by the last CTA of the group to exit,
+// i.e. after every CTA of the group has read it).
+// late_trigger: release the dependent kernel only after the wait.  Ranks that share one
+// device need it: with the early trigger the whole chain of later kernels of a CUDA graph
+// becomes resident (blocked in griddepcontrol.wait) and can fill the device while the peer
+// rank, whose push would unblock it, cannot get a CTA scheduled.
+unsigned long long g_xchg_timeout_ns = 20ull * 1000 * 1000 * 1000;
+constexpr int kXchgMaxPeers = 64;
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kXchgThreads)
+halo_exchange_kernel(int trace_slot, const XchgPeer* __restrict__ peers, double* vec, int ld, int k,
+                     size_t parity_stride, int* ctrl, unsigned long long timeout_ns, int late_trigger) {
+  trace_begin(trace_slot);
+  if (!late_trigger) pdl_launch_dependents();
+  const XchgPeer pr = peers[blockIdx.y];
+  int* arrive = ctrl + 8 + blockIdx.y;
+  int* leave = ctrl + 8 + kXchgMaxPeers + blockIdx.y;
+  int* group_epoch = ctrl + 8 + 2 * kXchgMaxPeers + blockIdx.y;
+  const int nthreads = gridDim.x * kXchgThreads;
+  pdl_wait();  // vec is final; the previous exchange kernel has completed
+  const int epoch = ld_acquire_gpu(group_epoch) + 1;
+  const size_t par = (epoch & 1) ? parity_stride : 0;
+  // (1) push
+  double* dst = pr.remote_slot + par;
+  for (int q = 0; q < k; q++)
+    for (int i = blockIdx.x * kXchgThreads + threadIdx.x; i < pr.n_send; i += nthreads)
+      dst[(size_t)q * pr.n_send + i] = ld_vec(vec + pr.send_idx[i] + (size_t)q * ld);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // (2) publish
+    if (atomicAdd(arrive, 1) == (int)gridDim.x - 1) {
+      atomicExch(arrive, 0);
+      __threadfence_system();
+      st_release_sys(pr.remote_flag, epoch);
+    }
+    // (3) wait for the peer; once any wait has timed out the context is poisoned and later
+    // exchanges do not wait again
+    const unsigned long long t0 = global_timer();
+    unsigned spins = 0;
+    while (ld_acquire_sys(pr.local_flag) - epoch < 0) {
+      if ((++spins & 1023u) == 0) {
+        if (ld_acquire_gpu(ctrl + 2) != 0) break;
+        if (global_timer() - t0 > timeout_ns) {
+          atomicExch(ctrl + 2, 1);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (late_trigger) pdl_launch_dependents();
+  // (4) scatter
+  const double* src = pr.local_slot + par;
+  for (int q = 0; q < k; q++)
+    for (int i = blockIdx.x * kXchgThreads + threadIdx.x; i < pr.n_recv; i += nthreads)
+      vec[pr.recv_idx[i] + (size_t)q * ld] = ld_relaxed_sys_f64(src + (size_t)q * pr.n_recv + i);
+  if (threadIdx.x == 0 && atomicAdd(leave, 1) == (int)gridDim.x - 1) {
+    atomicExch(leave, 0);
+    st_release_gpu(group_epoch, epoch);
   }
   trace_end(trace_slot);
 }
@@ -876,33 +966,35 @@ inline bool use_staged(const SellDev& M) {
 template <int MODE>
 void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, const double* b,
                   double* y, int ldy, double* z, int k, cudaStream_t st) {
-  if (M.nrows <= 0) return;
+  const int rb = M.row_begin(), re = M.row_end();
+  if (re <= rb) return;
+  const int span = re - (rb & ~31);  // rows covered by the grid (it starts at a slice boundary)
   constexpr int R = 4, W = 3;
   if (g_use_tma && M.max_width <= W && M.max_chunk32 > 0 &&
       static_cast<size_t>(M.max_chunk32) * 12 <= static_cast<size_t>(kStageCapBytes)) {
-    const int gs = blocks_for(M.nrows, kBlock * R);
+    const int gs = blocks_for(span, kBlock * R);
     SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<K, MODE, R, W>, gs, kBlock,
-                                    static_cast<size_t>(M.max_chunk32) * 12, st, M.nrows, M.nslices,
+                                    static_cast<size_t>(M.max_chunk32) * 12, st, rb, re, M.nslices,
                                     M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z));
     return;
   }
   // large levels, k = 1: two rows per thread (fewer, fatter CTAs; see the Gauss-Seidel kernel)
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && M.nrows >= 600000 &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= 600000 &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
-    launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(M.nrows, kBlock * 2),
-                  kBlock, static_cast<size_t>(M.max_chunk16) * 12, st, M.nrows, M.nslices, M.max_chunk16,
+    launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(span, kBlock * 2),
+                  kBlock, static_cast<size_t>(M.max_chunk16) * 12, st, rb, re, M.nslices, M.max_chunk16,
                   M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z);
     return;
   }
-  const int g = blocks_for(M.nrows, kBlock);
+  const int g = blocks_for(span, kBlock);
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, true>, g, kBlock, stage_bytes(M), st,
-                                    M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx,
+                                    rb, re, M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx,
                                     b, y, ldy, z));
   } else {
-    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, false>, g, kBlock, 0, st, M.nrows,
-                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx, b, y,
+    SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_kernel<K, MODE, false>, g, kBlock, 0, st, rb,
+                                    re, M.nslices, M.max_chunk, M.slice_ptr, M.col, v, x, ldx, b, y,
                                     ldy, z));
   }
 }
@@ -928,31 +1020,66 @@ void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, i
   launch_apply<MODE_ADD>(M, M.val, x, ldx, nullptr, u, ldu, nullptr, k, st);
 }
 
-int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows : 1, kBlock); }
+int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows + 32 : 1, kBlock); }
 
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st) {
-  int g = residual_norm_blocks(M.nrows);
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && M.nrows >= 600000 &&
+  const int rb = M.row_begin(), re = M.row_end();
+  const int span = re > rb ? re - (rb & ~31) : 0;
+  if (span <= 0) {  // a rank without rows on this level contributes 0
+    launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, 0, out);
+    return;
+  }
+  int g = blocks_for(span, kBlock);
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= 600000 &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
-    g = blocks_for(M.nrows, kBlock * 2);
+    g = blocks_for(span, kBlock * 2);
     launch_kernel("residual_norm", sell_apply_short_kernel<1, MODE_NORM, 2, kPre>, g, kBlock,
-                  static_cast<size_t>(M.max_chunk16) * 12, st, M.nrows, M.nslices, M.max_chunk16,
+                  static_cast<size_t>(M.max_chunk16) * 12, st, rb, re, M.nslices, M.max_chunk16,
                   M.slice_ptr, M.col, M.valT, x, ld, b, scratch, ld, nullptr);
     launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
     return;
   }
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
-                                    st, M.nrows, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
+                                    st, rb, re, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
                                     x, b, ld, scratch));
   } else {
-    SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, M.nrows,
-                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT, x, b, ld,
+    SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, rb,
+                                    re, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT, x, b, ld,
                                     scratch));
   }
   launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
+}
+
+void set_xchg_timeout_ms(long long ms) {
+  if (ms > 0) g_xchg_timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+}
+
+int xchg_ctrl_ints() { return 8 + 3 * kXchgMaxPeers; }
+int xchg_max_peers() { return kXchgMaxPeers; }
+
+void launch_halo_exchange(const XchgPeer* d_peers, int npeers, int ctas_per_peer, double* vec, int ld,
+                          int k, size_t parity_stride, int* ctrl, bool late_trigger, cudaStream_t st) {
+  if (npeers <= 0 || npeers > kXchgMaxPeers) return;
+  ctas_per_peer = std::max(1, std::min(ctas_per_peer, 32));
+  int slot = -1;
+  if (g_trace.on && g_trace.next < g_trace.cap) {
+    slot = g_trace.next++;
+    g_trace.names.push_back(g_trace.label + " halo_exchange g" + std::to_string(npeers * ctas_per_peer));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas_per_peer, npeers);
+  cfg.blockDim = dim3(kXchgThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, halo_exchange_kernel, slot, d_peers, vec, ld, k, parity_stride, ctrl,
+                     g_xchg_timeout_ns, late_trigger ? 1 : 0);
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
@@ -1507,6 +1634,62 @@ void launch_permute_out(const double* in, const int* perm, double* out, int n, i
                         cudaStream_t st) {
   if (n > 0) permute_out_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, perm, out, n, k);
 }
+// Force the (lazily loaded) solve-time kernels into the context now.  Loading a kernel may
+// synchronise the whole context; when ranks share a device that must not happen while
+// another rank already spins in a halo exchange.
+namespace {
+template <class F>
+void preload_one(F* f) {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, f);
+}
+template <int K>
+void preload_k() {
+  preload_one(sell_apply_kernel<K, MODE_SPMV, true>);
+  preload_one(sell_apply_kernel<K, MODE_SPMV, false>);
+  preload_one(sell_apply_kernel<K, MODE_RESIDUAL, true>);
+  preload_one(sell_apply_kernel<K, MODE_RESIDUAL, false>);
+  preload_one(sell_apply_kernel<K, MODE_ADD, true>);
+  preload_one(sell_apply_kernel<K, MODE_ADD, false>);
+  preload_one(sell_apply_kernel<K, MODE_SPMV_ZERO, true>);
+  preload_one(sell_apply_kernel<K, MODE_SPMV_ZERO, false>);
+  preload_one(sell_apply_short_kernel<K, MODE_SPMV, 4, 3>);
+  preload_one(sell_apply_short_kernel<K, MODE_RESIDUAL, 4, 3>);
+  preload_one(sell_apply_short_kernel<K, MODE_ADD, 4, 3>);
+  preload_one(sell_apply_short_kernel<K, MODE_SPMV_ZERO, 4, 3>);
+  preload_one(sell_residual_norm_kernel<K, true>);
+  preload_one(sell_residual_norm_kernel<K, false>);
+  preload_one(sell_gs_phase_kernel<K, true>);
+  preload_one(sell_gs_phase_kernel<K, false>);
+  preload_one(dense_sym_tile_kernel<K>);
+  preload_one(dense_sym_reduce_kernel<K>);
+}
+}  // namespace
+
+void preload_kernels() {
+  preload_k<1>();
+  preload_k<2>();
+  preload_k<3>();
+  preload_k<4>();
+  if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
+  preload_one(sell_gs_phase_multi_kernel<1, 2>);
+  preload_one(sell_gs_phase_multi_kernel<1, 4>);
+  preload_one(sell_apply_short_kernel<1, MODE_SPMV, 2, kPre>);
+  preload_one(sell_apply_short_kernel<1, MODE_RESIDUAL, 2, kPre>);
+  preload_one(sell_apply_short_kernel<1, MODE_ADD, 2, kPre>);
+  preload_one(sell_apply_short_kernel<1, MODE_SPMV_ZERO, 2, kPre>);
+  preload_one(sell_apply_short_kernel<1, MODE_NORM, 2, kPre>);
+  preload_one(reduce_partials_kernel);
+  preload_one(halo_exchange_kernel);
+  preload_one(fill_kernel);
+  preload_one(gather_system_kernel);
+  preload_one(scatter_solution_kernel);
+  preload_one(scatter_known_kernel);
+  preload_one(permute_in_kernel);
+  preload_one(permute_out_kernel);
+  cudaGetLastError();
+}
+
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
   if (n > 0) launch_kernel("fill", fill_kernel, blocks_for(n, 256), 256, 0, st, p, v, n);
 }

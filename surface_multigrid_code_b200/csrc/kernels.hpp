@@ -21,6 +21,17 @@ struct SellDev {
   const int* col = nullptr;
   const double* val = nullptr;
   const double* valT = nullptr;
+  // rows [rb, re) are processed (re < 0: all rows); a rank of a row-partitioned level
+  // applies only its own rows of the full matrix
+  int rb = 0, re = -1;
+  int row_begin() const { return rb; }
+  int row_end() const { return re < 0 ? nrows : re; }
+  SellDev rows(int b, int e) const {
+    SellDev d = *this;
+    d.rb = b;
+    d.re = e;
+    return d;
+  }
 };
 
 constexpr int kMaxK = 4;  // right-hand sides handled per kernel pass
@@ -103,6 +114,35 @@ struct GsFlow {
 // one Gauss-Seidel phase: rows [ps, pe) of the permuted matrix, in place on u
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,
                      int k, int ps, int pe, const GsFlow& flow, cudaStream_t st);
+
+// ---- multi-GPU halo exchange over peer-mapped memory ------------------------------------
+// One (exchange, peer) pair.  The sender gathers vec[send_idx[i]] into the PEER's staging
+// slot (a store over NVLink), publishes an epoch flag in the peer's memory, waits for the
+// peer's flag in its own memory and scatters its own staging slot into vec[recv_idx[i]].
+// Staging is double-buffered by epoch parity: a rank can be at most one exchange ahead of
+// a peer, because it cannot leave exchange e before the peer has entered it.
+struct XchgPeer {
+  int n_send = 0, n_recv = 0;
+  const int* send_idx = nullptr;
+  const int* recv_idx = nullptr;
+  double* remote_slot = nullptr;       // peer memory: parity 0; parity 1 at + parity_stride
+  const double* local_slot = nullptr;  // own memory, written by the peer
+  int* remote_flag = nullptr;          // peer memory
+  const int* local_flag = nullptr;     // own memory, written by the peer
+};
+constexpr int kXchgThreads = 512;
+// ints of control memory (zero-initialised) an exchange context needs
+int xchg_ctrl_ints();
+int xchg_max_peers();
+// how long an exchange waits for a peer before it gives up and poisons the context (20 s)
+void set_xchg_timeout_ms(long long ms);
+// vec (ld, k columns) is both source and destination; ctrl[2] != 0 after a wait timed out.
+// ctas_per_peer in 1..32 may differ from exchange to exchange.
+void launch_halo_exchange(const XchgPeer* d_peers, int npeers, int ctas_per_peer, double* vec, int ld,
+                          int k, size_t parity_stride, int* ctrl, bool late_trigger, cudaStream_t st);
+
+// load every solve-time kernel into the current context (see kernels.cu)
+void preload_kernels();
 
 // ---- setup-time numeric kernels ---------------------------------------------
 // out[i] = in[idx[i]]

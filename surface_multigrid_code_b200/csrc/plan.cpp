@@ -391,6 +391,24 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
     L.phase = greedy_colours(A, order, &L.n_phases);
   }
   if (n == 0) L.n_phases = 0;
+  if (L.nparts > 1 && L.layout != LAYOUT_PLAIN) {
+    // multi-GPU: group rows by (part, phase) or (phase, part); see LevelPlan::group
+    if (L.layout == LAYOUT_PARTITIONED && L.part.empty()) {
+      // finest partitioned level: equal chunks of the breadth-first order (strips of BFS fronts)
+      L.part.resize(n);
+      for (int t = 0; t < n; t++)
+        L.part[order[t]] = static_cast<int>(static_cast<int64_t>(t) * L.nparts / std::max(n, 1));
+    }
+    std::vector<int> grp(n);
+    for (int i = 0; i < n; i++) grp[i] = L.group(L.part[i], L.phase[i]);
+    L.order = make_row_order(A, grp, L.nparts * L.n_phases, rank, opt.sigma);
+    L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
+    remap_src(L.sellA, L.live_src);
+    L.blk_ofs.assign(1, 0);  // no dataflow schedule
+    return;
+  }
+  L.layout = LAYOUT_PLAIN;
+  L.nparts = 1;
   L.order = make_row_order(A, L.phase, L.n_phases, rank, opt.sigma);
   L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
   remap_src(L.sellA, L.live_src);
@@ -439,6 +457,90 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
           std::fprintf(stderr, "\n");
         }
       }
+    }
+  }
+}
+
+// ---- multi-GPU exchange lists ---------------------------------------------------------
+namespace {
+struct Need {
+  int dst, src, idx;
+  bool operator<(const Need& o) const {
+    return dst != o.dst ? dst < o.dst : (src != o.src ? src < o.src : idx < o.idx);
+  }
+  bool operator==(const Need& o) const { return dst == o.dst && src == o.src && idx == o.idx; }
+};
+Exchange make_exchange(std::vector<Need>& needs, int world) {
+  std::sort(needs.begin(), needs.end());
+  needs.erase(std::unique(needs.begin(), needs.end()), needs.end());
+  Exchange x;
+  x.idx.assign(static_cast<size_t>(world) * world, {});
+  for (const Need& nd : needs) x.idx[static_cast<size_t>(nd.src) * world + nd.dst].push_back(nd.idx);
+  return x;
+}
+}  // namespace
+
+// owner of a coarse row = owner of the fine row that carries the largest weight of its
+// prolongation column (for subdivision hierarchies: the fine copy of the coarse vertex)
+static std::vector<int> coarse_parts(const Csc& P, const std::vector<int>& fine_part) {
+  std::vector<int> part(P.cols, 0);
+  for (int c = 0; c < P.cols; c++) {
+    double best = -1.0;
+    for (int p = P.colptr[c]; p < P.colptr[c + 1]; p++) {
+      const double w = P.val[p] < 0 ? -P.val[p] : P.val[p];
+      if (w > best) {
+        best = w;
+        part[c] = fine_part[P.rowidx[p]];
+      }
+    }
+  }
+  return part;
+}
+
+static void plan_exchanges(Plan& pl, const std::vector<Csc>& Pz) {
+  const int W = pl.world;
+  const int nlev = static_cast<int>(pl.lv.size());
+  for (int l = 0; l < nlev; l++) {
+    LevelPlan& L = pl.lv[l];
+    if (L.nparts <= 1) continue;
+    const std::vector<int>& ip = L.order.iperm;
+    {  // every row of part src -> all other ranks
+      L.gather_all.idx.assign(static_cast<size_t>(W) * W, {});
+      std::vector<std::vector<int>> own(W);
+      for (int i = 0; i < L.n; i++) own[L.part[i]].push_back(ip[i]);
+      for (int s = 0; s < W; s++) {
+        std::sort(own[s].begin(), own[s].end());
+        for (int d = 0; d < W; d++)
+          if (d != s) L.gather_all.idx[static_cast<size_t>(s) * W + d] = own[s];
+      }
+    }
+    if (L.layout != LAYOUT_PARTITIONED) continue;
+    std::vector<Need> nu;
+    std::vector<std::vector<Need>> nup(L.n_phases);
+    for (int j = 0; j < L.n; j++)
+      for (int p = L.Alive.colptr[j]; p < L.Alive.colptr[j + 1]; p++) {
+        const int i = L.Alive.rowidx[p];  // symmetric pattern: row i reads column j
+        if (L.part[i] == L.part[j]) continue;
+        const Need nd{L.part[i], L.part[j], ip[j]};
+        nu.push_back(nd);
+        nup[L.phase[j]].push_back(nd);
+      }
+    L.halo_u = make_exchange(nu, W);
+    L.halo_u_phase.clear();
+    for (auto& v : nup) L.halo_u_phase.push_back(make_exchange(v, W));
+    if (l + 1 < nlev) {
+      LevelPlan& C = pl.lv[l + 1];  // PARTITIONED or SPLIT: C.part is set
+      const Csc& P = Pz[l + 1];     // rows: level l, columns: level l+1, zero-free
+      std::vector<Need> nr, npu;
+      for (int c = 0; c < P.cols; c++)
+        for (int p = P.colptr[c]; p < P.colptr[c + 1]; p++) {
+          const int f = P.rowidx[p];
+          if (L.part[f] == C.part[c]) continue;
+          nr.push_back(Need{C.part[c], L.part[f], ip[f]});                    // restriction row c reads r[f]
+          npu.push_back(Need{L.part[f], C.part[c], C.order.iperm[c]});        // prolongation row f reads u_c[c]
+        }
+      L.halo_r = make_exchange(nr, W);
+      if (C.layout == LAYOUT_PARTITIONED) C.halo_pu = make_exchange(npu, W);
     }
   }
 }
@@ -554,8 +656,26 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
     pl.lv[l].Alive = spgemm_pattern(Tz, Pz[l]);
     pl.lv[l].live_src = locate_entries(pl.lv[l].A, pl.lv[l].Alive);
   }
+  // multi-GPU: which levels are partitioned by rows
+  pl.world = std::max(1, opt.world);
+  pl.dist_levels = 0;
+  if (pl.world > 1) {
+    int nd = opt.dist_levels;
+    if (nd < 0) {
+      nd = 1;
+      while (nd < nlev - 1 &&
+             pl.lv[nd].A.cols >= static_cast<int64_t>(opt.dist_min_rows) * pl.world)
+        nd++;
+    }
+    pl.dist_levels = std::max(1, std::min(nd, nlev - 1));
+  }
   for (int l = 0; l < nlev; l++) {
     LevelPlan& L = pl.lv[l];
+    if (pl.world > 1 && l <= pl.dist_levels) {
+      L.nparts = pl.world;
+      L.layout = l < pl.dist_levels ? LAYOUT_PARTITIONED : LAYOUT_SPLIT;
+      if (l > 0) L.part = coarse_parts(Pz[l], pl.lv[l - 1].part);
+    }
     if (!pattern_symmetric(L.A, &L.tmap) || !pattern_symmetric(L.Alive, nullptr)) {
       pl.error = "sparsity pattern of the level matrix is not symmetric (level " +
                  std::to_string(l) + ")";
@@ -585,6 +705,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
       return SMG_E_UNSUPPORTED;
     }
   }
+  if (pl.world > 1) plan_exchanges(pl, Pz);
   return SMG_OK;
 }
 

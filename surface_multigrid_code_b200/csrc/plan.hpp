@@ -8,6 +8,7 @@
 // the hot path lives in kernels.cu; the only values touched here are the entries of
 // the prolongation matrices, which are copied / sliced, never combined.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -82,6 +83,30 @@ struct RowOrder {
 RowOrder make_row_order(const Csc& A, const std::vector<int>& phase, int n_phases,
                         const std::vector<int>& rank, int sigma);
 
+// ---- row partition across ranks (multi-GPU) --------------------------------------
+// One halo-exchange pattern of a level: idx[src * world + dst] = rows (permuted numbering of
+// the level, ascending) whose values rank `src` owns and rank `dst` reads.  The same list is
+// the sender's gather list and the receiver's scatter list.
+struct Exchange {
+  std::vector<std::vector<int>> idx;
+  bool empty() const {
+    for (const auto& v : idx)
+      if (!v.empty()) return false;
+    return true;
+  }
+  size_t max_count() const {
+    size_t m = 0;
+    for (const auto& v : idx) m = std::max(m, v.size());
+    return m;
+  }
+};
+enum LevelLayout {
+  LAYOUT_PLAIN = 0,       // rows ordered (phase, locality rank); every rank holds and computes all rows
+  LAYOUT_PARTITIONED = 1, // rows ordered (part, phase, rank); rank r computes part r only
+  LAYOUT_SPLIT = 2        // replicated level directly below a partitioned one: rows ordered
+                          // (phase, part, rank); part r's rows are what rank r restricts into
+};
+
 // ---- whole-hierarchy plan ----------------------------------------------------
 struct LevelPlan {
   int n = 0;
@@ -114,6 +139,23 @@ struct LevelPlan {
   Sell sellPT;                // rows: coarse level lv; y = PT x
   Csc T1;                     // pattern of PT * A_{lv-1}
   std::vector<int> t1_col;
+  // multi-GPU (PlanOptions::world > 1).  With nparts > 1 order.phase_ptr has
+  // nparts * n_phases + 1 entries: group (part, phase) for LAYOUT_PARTITIONED, (phase, part)
+  // for LAYOUT_SPLIT.
+  int layout = LAYOUT_PLAIN;
+  int nparts = 1;
+  std::vector<int> part;      // owner of every row (reference numbering)
+  Exchange halo_u;            // u read by the A rows of another part (PARTITIONED)
+  std::vector<Exchange> halo_u_phase;  // the same, split by the phase of the row sent
+  Exchange halo_r;            // r read by the PT rows (level lv+1) of another part (PARTITIONED)
+  Exchange halo_pu;           // this level's u read by prolongation rows (level lv-1) of another
+                              // part (PARTITIONED below PARTITIONED)
+  Exchange gather_all;        // every row of part src -> every other rank (PARTITIONED, SPLIT)
+  // rows of this rank's phases / of a whole part, in the permuted numbering
+  int group(int part_id, int phase_id) const {
+    return layout == LAYOUT_PARTITIONED ? part_id * n_phases + phase_id
+                                        : (layout == LAYOUT_SPLIT ? phase_id * nparts + part_id : phase_id);
+  }
 };
 
 struct PlanOptions {
@@ -121,6 +163,12 @@ struct PlanOptions {
   int locality_reorder = 1;
   int sigma = 256;
   int sort_cols = -1;  // -1: on for multicolour, off for wavefront (bit-parity order)
+  // multi-GPU: number of ranks the fine levels are partitioned over, and how many levels
+  // (from level 0) are partitioned; < 0: every level with at least dist_min_rows rows per
+  // rank (always level 0, never the coarsest)
+  int world = 1;
+  int dist_levels = -1;
+  int dist_min_rows = 100000;
 };
 
 struct Plan {
@@ -132,6 +180,8 @@ struct Plan {
   Csc Auk;                    // pattern, columns in caller order of `known`
   std::vector<int> auk_src;
   std::vector<LevelPlan> lv;
+  int world = 1;
+  int dist_levels = 0;  // levels 0 .. dist_levels-1 are PARTITIONED, level dist_levels is SPLIT
   std::string error;
 };
 

@@ -21,6 +21,7 @@
 // entry point fails with SMG_E_CUDA / SMG_E_STATE.
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -49,6 +50,13 @@ double now_ms() {
 }
 
 // ---- device buffers ----------------------------------------------------------
+// Stream-ordered allocation (cudaMallocAsync / cudaFreeAsync) on the stream of the handle
+// the calling thread is working on: cudaMalloc / cudaFree synchronise the whole device, and
+// a rank that is behind must never wait for the kernels of a rank that is ahead and already
+// spinning in a halo exchange (ranks may share a device).
+thread_local cudaStream_t tls_stream = nullptr;
+thread_local bool tls_async = false;
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -66,14 +74,18 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (tls_async) cudaFreeAsync(p, tls_stream);
+      else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    cudaError_t e = tls_async ? cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), tls_stream)
+                              : cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
     if (e == cudaSuccess) n = count;
     else p = nullptr;
     return e;
@@ -109,6 +121,14 @@ struct SellBufs {
   }
 };
 
+// one exchange pattern (plan.hpp::Exchange) as seen by this rank
+struct ExchDev {
+  DevBuf<smg::XchgPeer> peers;
+  std::vector<DevBuf<int>> lists;
+  bool any = false;  // some pair of ranks moves data (otherwise the exchange is skipped by all)
+  int ctas = 1;      // CTAs per peer: one per 4096 values of the longest list
+};
+
 struct LevelDev {
   int n = 0;
   // CSC of mg[l].A in reference order (pattern static, values numeric)
@@ -130,6 +150,42 @@ struct LevelDev {
   DevBuf<double> t_val;
   // work vectors (permuted numbering), n x kcap column-major, ld = n
   DevBuf<double> b, u, r;
+  // rows this rank smooths, one range per phase (all rows of the phase unless the level is
+  // row-partitioned), and the rows it applies operators to
+  std::vector<std::pair<int, int>> gs_ranges;
+  int layout = smg::LAYOUT_PLAIN;
+  int own_b = 0, own_e = 0;                          // PARTITIONED: this rank's rows
+  std::vector<std::pair<int, int>> restrict_ranges;  // rows of PT this rank computes
+  ExchDev x_halo_u, x_halo_r, x_halo_pu, x_gather;
+  std::vector<ExchDev> x_halo_u_phase;
+};
+
+// multi-GPU context: the comm buffer of every rank is mapped into every other rank
+struct DistCtx {
+  int rank = 0, world = 1;
+  bool connected = false;
+  int exact = 0;  // 1: halo exchange after every colour (same result as one GPU), 0: per sweep
+  size_t comm_bytes = 0, flags_bytes = 0, slot_doubles = 0;
+  char* comm = nullptr;
+  std::vector<char*> peer;    // world entries, peer[rank] == comm
+  std::vector<char> opened;   // peer[q] came from cudaIpcOpenMemHandle
+  DevBuf<int> ctrl;
+  DevBuf<double> normv;
+  ExchDev x_norm;
+  int64_t exchanges = 0;
+  bool shared_device = false;  // some other rank uses this device too (tests): late PDL trigger
+  bool failed = false;  // an exchange timed out: results are garbage, every later call fails
+};
+constexpr size_t kFlagStride = 128;
+
+struct DistBlob {  // what smg_dist_get_handle exports (smg_dist_handle_bytes() bytes)
+  cudaIpcMemHandle_t ipc;
+  long long pid;
+  unsigned long long ptr;
+  long long bytes;
+  int device;
+  int rank;
+  char uuid[16];  // of the device: two ranks on one physical GPU are detected by it
 };
 
 struct TailLists {
@@ -185,9 +241,15 @@ struct smg_handle {
   std::map<std::tuple<int, int, int, int, int>, TailLists> tails;  // (first level, pre, post, k0, kk)
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool no_prefetch = false;
+  bool async_alloc = false;
+  DistCtx dist;
+  int dist_levels = -1, dist_min_rows = 0;
 };
 
 namespace {
+
+bool dist_on(const smg_handle* h) { return h->dist.world > 1; }
 
 int fail(smg_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -224,7 +286,7 @@ void drop_graphs(smg_handle* h) {
 // first level of the V-cycle started at lv0 that runs inside the cluster tail kernel
 int tail_first_level(const smg_handle* h, int lv0) {
   const int last = static_cast<int>(h->lv.size()) - 1;
-  if (h->tail_cluster <= 0 || h->opt.tail_rows <= 0) return last;
+  if (h->tail_cluster <= 0 || h->opt.tail_rows <= 0 || dist_on(h)) return last;
   return std::min(last, std::max(lv0, h->tail_start));
 }
 
@@ -334,16 +396,109 @@ int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT
     out->max_width = std::max(out->max_width, (S.slice_ptr[s0 + 1] - S.slice_ptr[s0]) / 32);
     out->max_chunk16 = std::max(out->max_chunk16, S.slice_ptr[std::min(S.nslices, s0 + 16)] - S.slice_ptr[s0]);
     out->max_chunk32s = std::max(out->max_chunk32s, S.slice_ptr[std::min(S.nslices, s0 + 32)] - S.slice_ptr[s0]);
-    if (s0 % 32 == 0)
-      out->max_chunk32 = std::max(out->max_chunk32,
-                                  S.slice_ptr[std::min(S.nslices, s0 + 32)] - S.slice_ptr[s0]);
   }
+  // a row range may start at any slice (row-partitioned levels): any 32 consecutive slices
+  out->max_chunk32 = out->max_chunk32s;
   SMG_CUDA(h, out->slice_ptr.upload(S.slice_ptr, h->stream));
   SMG_CUDA(h, out->col.upload(S.col, h->stream));
   SMG_CUDA(h, out->src.upload(S.src, h->stream));
   SMG_CUDA(h, out->val.alloc(static_cast<size_t>(S.padded())));
   if (need_valT) SMG_CUDA(h, out->valT.alloc(static_cast<size_t>(S.padded())));
   else out->valT.release();
+  return SMG_OK;
+}
+
+// device-side view of one exchange pattern for this rank; peers in ascending rank order
+int build_exchange(smg_handle* h, const smg::Exchange& X, ExchDev* out) {
+  DistCtx& D = h->dist;
+  const int W = D.world, me = D.rank;
+  out->lists.clear();
+  out->any = !X.empty();
+  out->ctas = static_cast<int>(std::min<size_t>(32, std::max<size_t>(1, (X.max_count() + 4095) / 4096)));
+  if (X.idx.size() != static_cast<size_t>(W) * W) {
+    out->any = false;
+    return SMG_OK;
+  }
+  if (X.max_count() * smg::kMaxK > D.slot_doubles)
+    return fail(h, SMG_E_INVALID,
+                "halo exchange of " + std::to_string(X.max_count()) + " rows does not fit the comm buffer; "
+                "raise smg_dist_init's comm_bytes");
+  std::vector<smg::XchgPeer> peers;
+  for (int q = 0; q < W; q++) {
+    if (q == me) continue;
+    const std::vector<int>& snd = X.idx[static_cast<size_t>(me) * W + q];
+    const std::vector<int>& rcv = X.idx[static_cast<size_t>(q) * W + me];
+    smg::XchgPeer pr;
+    pr.n_send = static_cast<int>(snd.size());
+    pr.n_recv = static_cast<int>(rcv.size());
+    out->lists.emplace_back();
+    SMG_CUDA(h, out->lists.back().upload(snd, h->stream));
+    pr.send_idx = out->lists.back().p;
+    out->lists.emplace_back();
+    SMG_CUDA(h, out->lists.back().upload(rcv, h->stream));
+    pr.recv_idx = out->lists.back().p;
+    // slot s of a rank's staging area holds what rank s sent
+    pr.remote_slot = reinterpret_cast<double*>(D.peer[q] + D.flags_bytes) + static_cast<size_t>(me) * D.slot_doubles;
+    pr.local_slot = reinterpret_cast<const double*>(D.comm + D.flags_bytes) + static_cast<size_t>(q) * D.slot_doubles;
+    pr.remote_flag = reinterpret_cast<int*>(D.peer[q] + static_cast<size_t>(me) * kFlagStride);
+    pr.local_flag = reinterpret_cast<const int*>(D.comm + static_cast<size_t>(q) * kFlagStride);
+    peers.push_back(pr);
+  }
+  SMG_CUDA(h, out->peers.upload(peers, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+  return SMG_OK;
+}
+
+// ranges, exchange lists of every level for this rank (after upload of the matrices)
+int upload_dist(smg_handle* h) {
+  smg::Plan& pl = h->plan;
+  DistCtx& D = h->dist;
+  const int nlev = static_cast<int>(pl.lv.size());
+  for (int l = 0; l < nlev; l++) {
+    const smg::LevelPlan& P = pl.lv[l];
+    LevelDev& L = h->lv[l];
+    const std::vector<int>& pp = P.order.phase_ptr;
+    const int np = P.n_phases, W = P.nparts;
+    L.layout = P.layout;
+    L.gs_ranges.clear();
+    L.restrict_ranges.clear();
+    L.own_b = 0;
+    L.own_e = P.n;
+    if (P.layout == smg::LAYOUT_PARTITIONED) {
+      for (int p = 0; p < np; p++)
+        L.gs_ranges.emplace_back(pp[P.group(D.rank, p)], pp[P.group(D.rank, p) + 1]);
+      L.own_b = pp[static_cast<size_t>(D.rank) * np];
+      L.own_e = pp[static_cast<size_t>(D.rank + 1) * np];
+      L.restrict_ranges.emplace_back(L.own_b, L.own_e);
+    } else if (P.layout == smg::LAYOUT_SPLIT) {
+      for (int p = 0; p < np; p++) {
+        L.gs_ranges.emplace_back(pp[static_cast<size_t>(p) * W], pp[static_cast<size_t>(p + 1) * W]);
+        L.restrict_ranges.emplace_back(pp[P.group(D.rank, p)], pp[P.group(D.rank, p) + 1]);
+      }
+    } else {
+      for (int p = 0; p < np; p++) L.gs_ranges.emplace_back(pp[p], pp[p + 1]);
+      L.restrict_ranges.emplace_back(0, P.n);
+    }
+    if (!dist_on(h)) continue;
+    if (P.nparts > 1) SMG_TRY(build_exchange(h, P.gather_all, &L.x_gather));
+    if (P.layout == smg::LAYOUT_PARTITIONED) {
+      SMG_TRY(build_exchange(h, P.halo_u, &L.x_halo_u));
+      SMG_TRY(build_exchange(h, P.halo_r, &L.x_halo_r));
+      SMG_TRY(build_exchange(h, P.halo_pu, &L.x_halo_pu));
+      L.x_halo_u_phase.clear();
+      L.x_halo_u_phase.resize(P.halo_u_phase.size());
+      for (size_t p = 0; p < P.halo_u_phase.size(); p++)
+        SMG_TRY(build_exchange(h, P.halo_u_phase[p], &L.x_halo_u_phase[p]));
+    }
+  }
+  if (dist_on(h)) {  // partial sums of the residual norm: slot s of the row <- rank s
+    smg::Exchange X;
+    X.idx.assign(static_cast<size_t>(D.world) * D.world, {});
+    for (int s = 0; s < D.world; s++)
+      for (int d = 0; d < D.world; d++)
+        if (s != d) X.idx[static_cast<size_t>(s) * D.world + d] = {s};
+    SMG_TRY(build_exchange(h, X, &D.x_norm));
+  }
   return SMG_OK;
 }
 
@@ -361,18 +516,35 @@ int ensure_k(smg_handle* h, int k) {
   return SMG_OK;
 }
 
+// ---- multi-GPU helpers ------------------------------------------------------------
+// collective: every rank runs the same sequence of exchanges (kernels.hpp::XchgPeer)
+void exchange(smg_handle* h, ExchDev& X, double* vec, int ld, int k) {
+  if (!dist_on(h) || !X.any) return;
+  DistCtx& D = h->dist;
+  for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+    const int kk = std::min(smg::kMaxK, k - k0);
+    smg::launch_halo_exchange(X.peers.p, D.world - 1, X.ctas, vec + static_cast<size_t>(k0) * ld, ld,
+                              kk, D.slot_doubles * D.world, D.ctrl.p, D.shared_device, h->stream);
+    h->launches++;
+    D.exchanges++;
+  }
+}
+
 // ---- device-side operators on the level work vectors ---------------------------
+// On a row-partitioned level every operator touches this rank's rows only; the halo
+// exchanges that make the result usable by the next operator are issued here too.
 void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, int k) {
   LevelDev& L = h->lv[l];
   const SellDev A = L.sellA.view();
-  const int np = static_cast<int>(L.phase_ptr.size()) - 1;
+  const int np = static_cast<int>(L.gs_ranges.size());
+  const bool part = dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED;
   int p_first = -1, p_last = -1;  // non-empty phases
   for (int p = 0; p < np; p++)
-    if (L.phase_ptr[p + 1] > L.phase_ptr[p]) {
+    if (L.gs_ranges[p].second > L.gs_ranges[p].first) {
       if (p_first < 0) p_first = p;
       p_last = p;
     }
-  if (p_first < 0 || iters <= 0) return;
+  if (iters <= 0 || (p_first < 0 && !part)) return;
   smg::GsFlow flow;
   flow.mode = L.dataflow && (p_last > p_first || iters > 1) ? 1 : 0;
   flow.np = np;
@@ -385,36 +557,50 @@ void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, i
   // (its own epoch range) per group of kMaxK columns
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
-    for (int it = 0; it < iters; it++)
+    double* uu = u + static_cast<size_t>(k0) * L.n;
+    for (int it = 0; it < iters; it++) {
       for (int p = 0; p < np; p++) {
-        if (L.phase_ptr[p + 1] <= L.phase_ptr[p]) continue;
-        flow.p = p;
-        flow.it = it;
-        flow.first = it == 0 && p == p_first;
-        flow.last = it == iters - 1 && p == p_last;
-        // next non-empty phase of this call (its matrix chunk is prefetched into L2)
-        flow.pf_slice0 = -1;
-        if (!flow.last && h->opt.reserved[0] == 0) {
-          int q = p;
-          do q = (q + 1) % np; while (L.phase_ptr[q + 1] <= L.phase_ptr[q]);
-          flow.pf_slice0 = L.phase_ptr[q] >> 5;
-          flow.pf_slice_end = (L.phase_ptr[q + 1] + 31) >> 5;
+        const int ps = L.gs_ranges[p].first, pe = L.gs_ranges[p].second;
+        if (pe > ps) {
+          flow.p = p;
+          flow.it = it;
+          flow.first = it == 0 && p == p_first;
+          flow.last = it == iters - 1 && p == p_last;
+          // next non-empty phase of this call (its matrix chunk is prefetched into L2)
+          flow.pf_slice0 = -1;
+          if (!flow.last && !h->no_prefetch) {
+            int q = p;
+            do q = (q + 1) % np; while (L.gs_ranges[q].second <= L.gs_ranges[q].first);
+            flow.pf_slice0 = L.gs_ranges[q].first >> 5;
+            flow.pf_slice_end = (L.gs_ranges[q].second + 31) >> 5;
+          }
+          smg::launch_gs_phase(A, L.diag.p, b + static_cast<size_t>(k0) * L.n, uu, L.n, kk, ps, pe,
+                               flow, h->stream);
+          h->launches++;
         }
-        smg::launch_gs_phase(A, L.diag.p, b + static_cast<size_t>(k0) * L.n,
-                             u + static_cast<size_t>(k0) * L.n, L.n, kk, L.phase_ptr[p],
-                             L.phase_ptr[p + 1], flow, h->stream);
-        h->launches++;
+        // exact mode: the rows of this colour reach the other ranks before the next colour
+        if (part && h->dist.exact) exchange(h, L.x_halo_u_phase[p], uu, L.n, kk);
       }
+      // hybrid mode: Gauss-Seidel inside a rank, one halo exchange per sweep across ranks
+      if (part && !h->dist.exact) exchange(h, L.x_halo_u, uu, L.n, kk);
+    }
   }
+}
+
+// the matrix restricted to the rows this rank applies on level l
+SellDev own_rows(const smg_handle* h, const LevelDev& L, const SellDev& M) {
+  if (dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED) return M.rows(L.own_b, L.own_e);
+  return M;
 }
 
 void residual_device(smg_handle* h, int l, const double* b, const double* u, double* r, int k) {
   LevelDev& L = h->lv[l];
   if (L.n <= 0) return;
+  const SellDev A = own_rows(h, L, L.sellA.view());
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L.n;
-    smg::launch_residual(L.sellA.view(), b + o, u + o, r + o, L.n, kk, h->stream);
+    smg::launch_residual(A, b + o, u + o, r + o, L.n, kk, h->stream);
     h->launches++;
   }
 }
@@ -422,42 +608,64 @@ void residual_device(smg_handle* h, int l, const double* b, const double* u, dou
 void apply_A_device(smg_handle* h, int l, const double* u, double* y, int k) {
   LevelDev& L = h->lv[l];
   if (L.n <= 0) return;
+  const SellDev A = own_rows(h, L, L.sellA.view());
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L.n;
-    smg::launch_spmv(L.sellA.view(), true, u + o, L.n, y + o, L.n, kk, h->stream);
+    smg::launch_spmv(A, true, u + o, L.n, y + o, L.n, kk, h->stream);
     h->launches++;
   }
 }
 
-// x on level l (fine), y on level l+1; zero != nullptr: also zero[...] = 0 (same shape as y)
+// x on level l (fine), y on level l+1; zero != nullptr: also zero[...] = 0 (same shape as y).
+// Partitioned fine level: x must carry valid halo_r values; every rank computes the rows of
+// its part, and a replicated coarse level is completed with an all-gather.
 void restrict_device(smg_handle* h, int l, const double* x, double* y, int k, double* zero = nullptr) {
   LevelDev& F = h->lv[l];
   LevelDev& C = h->lv[l + 1];
   if (C.n <= 0) return;
+  const bool part = dist_on(h) && F.layout == smg::LAYOUT_PARTITIONED;
+  if (part && zero) {  // the halo rows of the coarse guess are zero too
+    smg::launch_fill(zero, 0.0, static_cast<int64_t>(C.n) * k, h->stream);
+    h->launches++;
+  }
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const double* xx = x + static_cast<size_t>(k0) * F.n;
     const size_t oc = static_cast<size_t>(k0) * C.n;
+    if (part) {
+      for (const auto& rg : C.restrict_ranges) {
+        if (rg.second <= rg.first) continue;
+        smg::launch_spmv(C.sellPT.view().rows(rg.first, rg.second), false, xx, F.n, y + oc, C.n, kk,
+                         h->stream);
+        h->launches++;
+      }
+      continue;
+    }
     if (zero) smg::launch_spmv_zero(C.sellPT.view(), xx, F.n, y + oc, zero + oc, C.n, kk, h->stream);
     else smg::launch_spmv(C.sellPT.view(), false, xx, F.n, y + oc, C.n, kk, h->stream);
     h->launches++;
   }
+  if (part && C.layout == smg::LAYOUT_SPLIT) exchange(h, C.x_gather, y, C.n, k);
 }
 
 // y (level l) = P x (level l+1)   /   u (level l) += P x
-void prolong_device(smg_handle* h, int l, const double* x, double* y, int k, bool add) {
+void prolong_device(smg_handle* h, int l, double* x, double* y, int k, bool add) {
   LevelDev& F = h->lv[l];
   LevelDev& C = h->lv[l + 1];
   if (F.n <= 0) return;
+  const bool part = dist_on(h) && F.layout == smg::LAYOUT_PARTITIONED;
+  if (part && C.layout == smg::LAYOUT_PARTITIONED) exchange(h, C.x_halo_pu, x, C.n, k);
+  const SellDev P = own_rows(h, F, C.sellP.view());
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
     const double* xx = x + static_cast<size_t>(k0) * C.n;
     double* yy = y + static_cast<size_t>(k0) * F.n;
-    if (add) smg::launch_prolong_add(C.sellP.view(), xx, C.n, yy, F.n, kk, h->stream);
-    else smg::launch_spmv(C.sellP.view(), false, xx, C.n, yy, F.n, kk, h->stream);
+    if (add) smg::launch_prolong_add(P, xx, C.n, yy, F.n, kk, h->stream);
+    else smg::launch_spmv(P, false, xx, C.n, yy, F.n, kk, h->stream);
     h->launches++;
   }
+  if (part && add) exchange(h, F.x_halo_u, y, F.n, k);  // the corrected halo rows of the neighbours
 }
 
 void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
@@ -484,6 +692,7 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     smg::trace_label(label);
     relax_device(h, l, pre, L.b.p, L.u.p, k);              // :36
     residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
+    if (dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED) exchange(h, L.x_halo_r, L.r.p, L.n, k);
     restrict_device(h, l, L.r.p, C.b.p, k, C.u.p);         // :44 and uc = 0 (:46-47), fused
   }
   if (ts < last) {  // levels ts .. last-1, down leg, inside one cluster
@@ -548,6 +757,8 @@ int vcycle_run(smg_handle* h, int lv0, int pre, int post, int k) {
 int residual_norm_device(smg_handle* h, int l, const double* b, const double* u, int k,
                          double* out_host) {
   LevelDev& L = h->lv[l];
+  DistCtx& D = h->dist;
+  const bool part = dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED;
   const int nb = smg::residual_norm_blocks(L.n);
   const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
   SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(nb)));
@@ -556,13 +767,34 @@ int residual_norm_device(smg_handle* h, int l, const double* b, const double* u,
     *out_host = 0.0;
     return SMG_OK;
   }
+  if (part) SMG_CUDA(h, D.normv.reserve(static_cast<size_t>(D.world) * std::max(nchunks, 16)));
+  const SellDev A = own_rows(h, L, L.sellA.view());
   for (int c = 0; c < nchunks; c++) {
     const int k0 = c * smg::kMaxK;
     const int kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L.n;
-    smg::launch_residual_norm2(L.sellA.view(), b + o, u + o, L.n, kk, h->norm_scratch.p,
-                               h->norm_out.p + c, h->stream);
+    // partitioned: the sum over this rank's rows lands in slot `rank` of the chunk's row
+    double* out = part ? D.normv.p + static_cast<size_t>(c) * D.world + D.rank : h->norm_out.p + c;
+    smg::launch_residual_norm2(A, b + o, u + o, L.n, kk, h->norm_scratch.p, out, h->stream);
     h->launches += 2;
+    if (part) exchange(h, D.x_norm, D.normv.p + static_cast<size_t>(c) * D.world, D.world, 1);
+  }
+  if (part) {
+    // every rank adds the same partial sums in rank order: identical residuals everywhere
+    int* xflag = reinterpret_cast<int*>(h->h_norm + 48);
+    SMG_CUDA(h, cudaMemcpyAsync(h->h_norm + 64, D.normv.p, sizeof(double) * nchunks * D.world,
+                                cudaMemcpyDeviceToHost, h->stream));
+    SMG_CUDA(h, cudaMemcpyAsync(xflag, D.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (*xflag) {
+      D.failed = true;
+      return fail(h, SMG_E_INTERNAL, "halo exchange: a wait for a peer rank timed out");
+    }
+    double ss = 0.0;
+    for (int c = 0; c < nchunks; c++)
+      for (int q = 0; q < D.world; q++) ss += h->h_norm[64 + static_cast<size_t>(c) * D.world + q];
+    *out_host = std::sqrt(ss);
+    return SMG_OK;
   }
   SMG_CUDA(h, cudaMemcpyAsync(h->h_norm, h->norm_out.p, sizeof(double) * nchunks,
                               cudaMemcpyDeviceToHost, h->stream));
@@ -676,7 +908,7 @@ int upload_plan(smg_handle* h) {
     SMG_CUDA(h, L.diag.alloc(static_cast<size_t>(P.n)));
     SMG_CUDA(h, L.perm.upload(P.order.perm, st));
     L.phase_ptr = P.order.phase_ptr;
-    L.dataflow = h->opt.dataflow && h->opt.smoother == SMG_SMOOTHER_MULTICOLOUR && P.n_phases >= 2 &&
+    L.dataflow = !dist_on(h) && h->opt.dataflow && h->opt.smoother == SMG_SMOOTHER_MULTICOLOUR && P.n_phases >= 2 &&
                  !P.dep_lo.empty();
     if (L.dataflow) {
       std::vector<int2> dep(P.dep_lo.size());
@@ -770,7 +1002,16 @@ int upload_plan(smg_handle* h) {
   }
   SMG_TRY(check_launch(h, "upload plan"));
   SMG_CUDA(h, cudaStreamSynchronize(st));  // host vectors above go out of scope
-  return SMG_OK;
+  return upload_dist(h);
+}
+
+void drop_graphs_if_device(smg_handle* h) {
+  if (!h->plan_only && h->device >= 0) {
+    cudaSetDevice(h->device);
+    tls_stream = h->stream;
+    tls_async = h->async_alloc;
+    drop_graphs(h);
+  }
 }
 
 int check_ready(const smg_handle* h, bool need_device) {
@@ -778,12 +1019,30 @@ int check_ready(const smg_handle* h, bool need_device) {
   if (!h->have_plan) return fail(const_cast<smg_handle*>(h), SMG_E_STATE, "smg_precompute has not been called");
   if (need_device && h->plan_only)
     return fail(const_cast<smg_handle*>(h), SMG_E_STATE, "plan-only handle (SMG_DEVICE_NONE) cannot compute");
+  if (need_device && h->dist.failed)
+    return fail(const_cast<smg_handle*>(h), SMG_E_INTERNAL, "a halo exchange timed out earlier on this handle");
   return SMG_OK;
 }
 
 int set_device(smg_handle* h) {
   if (h->plan_only) return SMG_OK;
   SMG_CUDA(h, cudaSetDevice(h->device));
+  tls_stream = h->stream;
+  tls_async = h->async_alloc;
+  return SMG_OK;
+}
+
+// an exchange wait that timed out (a peer rank died or never made the matching call)
+int check_exchange(smg_handle* h) {
+  if (!dist_on(h)) return SMG_OK;
+  int* flag = reinterpret_cast<int*>(h->h_norm + 48);
+  *flag = 0;
+  SMG_CUDA(h, cudaMemcpyAsync(flag, h->dist.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (*flag) {
+    h->dist.failed = true;
+    return fail(h, SMG_E_INTERNAL, "halo exchange: a wait for a peer rank timed out");
+  }
   return SMG_OK;
 }
 
@@ -808,6 +1067,7 @@ int stage_out(smg_handle* h, int l, const double* src, DevBuf<double>& stage, do
   h->launches++;
   SMG_CUDA(h, cudaMemcpyAsync(host, stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  SMG_TRY(check_exchange(h));
   return check_launch(h, "stage_out");
 }
 
@@ -834,6 +1094,13 @@ int check_dataflow(smg_handle* h) {
   for (int i = 0; i < n; i++) bad |= flags[i];
   if (bad) return fail(h, SMG_E_INTERNAL, "dataflow smoother: a device-side wait timed out");
   return SMG_OK;
+}
+
+// multi-GPU: a level vector whose rows were computed by their owners only -> complete on
+// every rank (collective)
+void complete_rows(smg_handle* h, int l, double* vec, int k) {
+  LevelDev& L = h->lv[l];
+  if (dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED) exchange(h, L.x_gather, vec, L.n, k);
 }
 
 // min_quad_with_fixed_mg_solve on device pointers
@@ -866,6 +1133,7 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
   }
   if (h->opt.verbose) std::printf("residual norm: %.17g\n", residual);
   // z(unknown) = z_unknown ; z(known) = known_val   (cpp:353-355)
+  complete_rows(h, 0, L0.u.p, k);  // multi-GPU: every rank returns the whole solution
   smg::launch_scatter_solution(L0.u.p, h->g.p, d_z, pl.n, nu, k, h->stream);
   h->launches++;
   if (pl.has_fixed && h->n_known_distinct > 0) {
@@ -876,6 +1144,7 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
   }
   SMG_TRY(check_launch(h, "solve"));
   SMG_TRY(check_dataflow(h));
+  SMG_TRY(check_exchange(h));
   *n_his = nh;
   *converged = residual > tol ? 0 : 1;  // cpp:357-360 (stale residual, by design)
   return SMG_OK;
@@ -983,15 +1252,31 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   h->device = dev;
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
   if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
-  if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->opt.reserved[0] = (e[0] && e[0] != '0');
+  if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->no_prefetch = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_DATAFLOW")) h->opt.dataflow = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_TAIL_ROWS")) h->opt.tail_rows = std::atoi(e);
   h->tail_cluster = h->opt.tail_rows > 0 ? smg::tail_cluster_size() : 0;
   if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 64 * sizeof(double)) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 1024 * sizeof(double)) != cudaSuccess) {
     smg_destroy(h);
     return SMG_E_CUDA;
+  }
+  {  // stream-ordered allocation when the device has memory pools (see DevBuf)
+    int pools = 0;
+    cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, dev);
+    if (const char* e = std::getenv("SMG_NO_ASYNC_ALLOC")) pools = pools && !(e[0] && e[0] != '0');
+    if (pools) {
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;  // freed blocks stay in the pool
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        h->async_alloc = true;
+      }
+    }
+    cudaGetLastError();
+    tls_stream = h->stream;
+    tls_async = h->async_alloc;
   }
   if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS ||
       cusolverDnSetStream(h->cusolver, h->stream) != CUSOLVER_STATUS_SUCCESS) {
@@ -1006,6 +1291,8 @@ void smg_destroy(smg_handle* h) {
   if (!h) return;
   if (!h->plan_only && h->device >= 0) {
     cudaSetDevice(h->device);
+    tls_stream = h->stream;
+    tls_async = h->async_alloc && h->stream;
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graphs(h);
     if (h->cusolver) cusolverDnDestroy(h->cusolver);
@@ -1018,7 +1305,16 @@ void smg_destroy(smg_handle* h) {
     h->ainv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
     h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
+    DistCtx& D = h->dist;
+    D.ctrl.release(); D.normv.release(); D.x_norm = ExchDev();
+    for (size_t q = 0; q < D.peer.size(); q++)
+      if (D.opened[q] && D.peer[q]) cudaIpcCloseMemHandle(D.peer[q]);
+    if (h->stream) cudaStreamSynchronize(h->stream);  // the frees above are stream-ordered
+    if (D.comm) cudaFree(D.comm);
+    D.comm = nullptr;
     if (h->stream) cudaStreamDestroy(h->stream);
+    tls_stream = nullptr;
+    tls_async = false;  // anything the destructor below still frees goes through cudaFree
   }
   delete h;
 }
@@ -1060,6 +1356,11 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   po.smoother = h->opt.smoother;
   po.locality_reorder = h->opt.locality_reorder;
   po.sigma = h->opt.sigma > 0 ? h->opt.sigma : 1;
+  po.world = h->dist.world;
+  po.dist_levels = h->dist_levels;
+  if (h->dist_min_rows > 0) po.dist_min_rows = h->dist_min_rows;
+  if (dist_on(h) && !h->plan_only && !h->dist.connected)
+    return fail(h, SMG_E_STATE, "smg_dist_connect has not been called");
   const int rc = smg::build_plan(A, known, n_known, h->P_full, po, &h->plan);
   if (rc != SMG_OK) return fail(h, rc, h->plan.error);
   const double t1 = now_ms();
@@ -1074,6 +1375,21 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
                               h->stream));
   SMG_TRY(numeric_setup(h));
+  if (dist_on(h)) {
+    // No allocation between collective calls (up to kMaxK right-hand sides): growing the
+    // memory pool can synchronise the device, which a rank that shares its device with a
+    // rank already spinning in an exchange must not do.
+    h->have_plan = true;
+    SMG_TRY(ensure_k(h, smg::kMaxK));
+    const size_t cnt = static_cast<size_t>(h->plan.n) * smg::kMaxK;
+    SMG_CUDA(h, h->st_a.reserve(cnt));
+    SMG_CUDA(h, h->st_b.reserve(cnt));
+    SMG_CUDA(h, h->st_c.reserve(cnt));
+    SMG_CUDA(h, h->st_d.reserve(std::max<size_t>(h->plan.known.size(), 1) * smg::kMaxK));
+    SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(h->lv[0].n))));
+    SMG_CUDA(h, h->norm_out.reserve(16));
+    SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   h->timings[4] = now_ms() - t1;
   h->have_plan = true;
   return SMG_OK;
@@ -1156,6 +1472,8 @@ int smg_vcycle(smg_handle* h, int lv, int pre, int post, const double* B, double
   SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
   SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
   SMG_TRY(vcycle_run(h, lv, pre, post, k));
+  complete_rows(h, lv, L.u.p, k);
+  SMG_TRY(check_exchange(h));
   return stage_out(h, lv, L.u.p, h->st_a, u, k);
 }
 
@@ -1169,6 +1487,7 @@ int smg_relax(smg_handle* h, int lv, int iters, const double* B, double* u, int 
   SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
   SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
   relax_device(h, lv, iters, L.b.p, L.u.p, k);
+  complete_rows(h, lv, L.u.p, k);
   return stage_out(h, lv, L.u.p, h->st_a, u, k);
 }
 
@@ -1181,6 +1500,7 @@ int smg_apply_A(smg_handle* h, int lv, const double* u, double* Au, int k) {
   LevelDev& L = h->lv[lv];
   SMG_TRY(stage_in(h, lv, u, h->st_a, L.u.p, k));
   apply_A_device(h, lv, L.u.p, L.r.p, k);
+  complete_rows(h, lv, L.r.p, k);
   return stage_out(h, lv, L.r.p, h->st_a, Au, k);
 }
 
@@ -1194,6 +1514,7 @@ int smg_residual(smg_handle* h, int lv, const double* B, const double* u, double
   SMG_TRY(stage_in(h, lv, B, h->st_a, L.b.p, k));
   SMG_TRY(stage_in(h, lv, u, h->st_b, L.u.p, k));
   residual_device(h, lv, L.b.p, L.u.p, L.r.p, k);
+  complete_rows(h, lv, L.r.p, k);
   return stage_out(h, lv, L.r.p, h->st_a, r, k);
 }
 
@@ -1218,6 +1539,7 @@ int smg_restrict(smg_handle* h, int lv, const double* x, double* Rx, int k) {
   SMG_TRY(ensure_k(h, k));
   SMG_TRY(stage_in(h, lv, x, h->st_a, h->lv[lv].r.p, k));
   restrict_device(h, lv, h->lv[lv].r.p, h->lv[lv + 1].b.p, k);
+  complete_rows(h, lv + 1, h->lv[lv + 1].b.p, k);
   return stage_out(h, lv + 1, h->lv[lv + 1].b.p, h->st_a, Rx, k);
 }
 
@@ -1229,6 +1551,7 @@ int smg_prolong(smg_handle* h, int lv, const double* x, double* Px, int k) {
   SMG_TRY(ensure_k(h, k));
   SMG_TRY(stage_in(h, lv + 1, x, h->st_a, h->lv[lv + 1].u.p, k));
   prolong_device(h, lv, h->lv[lv + 1].u.p, h->lv[lv].r.p, k, false);
+  complete_rows(h, lv, h->lv[lv].r.p, k);
   return stage_out(h, lv, h->lv[lv].r.p, h->st_a, Px, k);
 }
 
@@ -1243,6 +1566,183 @@ int smg_coarse_solve(smg_handle* h, const double* B, double* u, int k) {
   SMG_TRY(stage_in(h, last, u, h->st_b, L.u.p, k));
   coarse_solve_device(h, L.b.p, L.u.p, k);
   return stage_out(h, last, L.u.p, h->st_a, u, k);
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------
+int smg_dist_init(smg_handle* h, int rank, int world, size_t comm_bytes) {
+  if (!h) return SMG_E_INVALID;
+  if (world < 1 || world > smg::xchg_max_peers() || rank < 0 || rank >= world) return fail(h, SMG_E_INVALID, "bad rank / world");
+  DistCtx& D = h->dist;
+  if (D.comm || D.connected) return fail(h, SMG_E_STATE, "smg_dist_init was already called");
+  D.rank = rank;
+  D.world = world;
+  h->have_plan = false;
+  if (world == 1 || h->plan_only) return SMG_OK;
+  SMG_TRY(set_device(h));
+  if (comm_bytes == 0) comm_bytes = size_t(256) << 20;
+  D.flags_bytes = ((static_cast<size_t>(world) * kFlagStride + 1023) / 1024) * 1024;
+  if (comm_bytes < D.flags_bytes + static_cast<size_t>(world) * 2 * 4096)
+    return fail(h, SMG_E_INVALID, "comm_bytes too small");
+  D.slot_doubles = ((comm_bytes - D.flags_bytes) / sizeof(double) / (2 * static_cast<size_t>(world))) & ~size_t(31);
+  D.comm_bytes = comm_bytes;
+  smg::preload_kernels();
+  if (const char* e = std::getenv("SMG_XCHG_TIMEOUT_MS")) smg::set_xchg_timeout_ms(std::atoll(e));
+  SMG_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&D.comm), comm_bytes));
+  SMG_CUDA(h, cudaMemsetAsync(D.comm, 0, comm_bytes, h->stream));
+  SMG_CUDA(h, D.ctrl.upload(std::vector<int>(static_cast<size_t>(smg::xchg_ctrl_ints()), 0), h->stream));
+  SMG_CUDA(h, D.normv.upload(std::vector<double>(static_cast<size_t>(world) * 16, 0.0), h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMG_OK;
+}
+
+int smg_dist_handle_bytes(void) { return static_cast<int>(sizeof(DistBlob)); }
+
+int smg_dist_get_handle(smg_handle* h, void* blob) {
+  if (!h || !blob) return SMG_E_INVALID;
+  DistCtx& D = h->dist;
+  if (!D.comm) return fail(h, SMG_E_STATE, "smg_dist_init (world > 1, with a device) has not been called");
+  SMG_TRY(set_device(h));
+  DistBlob b;
+  std::memset(&b, 0, sizeof(b));
+  SMG_CUDA(h, cudaIpcGetMemHandle(&b.ipc, D.comm));
+  b.pid = static_cast<long long>(getpid());
+  b.ptr = reinterpret_cast<unsigned long long>(D.comm);
+  b.bytes = static_cast<long long>(D.comm_bytes);
+  b.device = h->device;
+  b.rank = D.rank;
+  cudaDeviceProp prop;
+  SMG_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+  std::memcpy(b.uuid, prop.uuid.bytes, 16);
+  std::memcpy(blob, &b, sizeof(b));
+  return SMG_OK;
+}
+
+int smg_dist_connect(smg_handle* h, const void* all_blobs) {
+  if (!h || !all_blobs) return SMG_E_INVALID;
+  DistCtx& D = h->dist;
+  if (D.world == 1) return SMG_OK;
+  if (!D.comm) return fail(h, SMG_E_STATE, "smg_dist_init has not been called");
+  if (D.connected) return fail(h, SMG_E_STATE, "already connected");
+  SMG_TRY(set_device(h));
+  D.peer.assign(static_cast<size_t>(D.world), nullptr);
+  D.opened.assign(static_cast<size_t>(D.world), 0);
+  const long long me = static_cast<long long>(getpid());
+  DistBlob mine;
+  std::memcpy(&mine, static_cast<const char*>(all_blobs) + static_cast<size_t>(D.rank) * sizeof(DistBlob), sizeof(mine));
+  for (int q = 0; q < D.world; q++) {
+    DistBlob b;
+    std::memcpy(&b, static_cast<const char*>(all_blobs) + static_cast<size_t>(q) * sizeof(DistBlob), sizeof(b));
+    if (b.rank != q || b.bytes != static_cast<long long>(D.comm_bytes))
+      return fail(h, SMG_E_INVALID, "blob " + std::to_string(q) + " does not match (rank order / comm_bytes)");
+    if (q != D.rank && std::memcmp(b.uuid, mine.uuid, 16) == 0) D.shared_device = true;
+    if (q == D.rank) {
+      D.peer[q] = D.comm;
+    } else if (b.pid == me) {  // a rank in this process: plain peer access
+      if (b.device != h->device) {
+        int can = 0;
+        SMG_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, b.device));
+        if (!can) return fail(h, SMG_E_UNSUPPORTED, "no peer access between the devices of two ranks");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(h, SMG_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      D.peer[q] = reinterpret_cast<char*>(b.ptr);
+    } else {
+      void* p = nullptr;
+      SMG_CUDA(h, cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      D.peer[q] = static_cast<char*>(p);
+      D.opened[q] = 1;
+    }
+  }
+  D.connected = true;
+  return SMG_OK;
+}
+
+int smg_dist_set_options(smg_handle* h, int exact, int dist_levels, int dist_min_rows) {
+  if (!h) return SMG_E_INVALID;
+  h->dist.exact = exact ? 1 : 0;
+  h->dist_levels = dist_levels;
+  h->dist_min_rows = dist_min_rows;
+  if (h->have_plan) drop_graphs_if_device(h);
+  return SMG_OK;
+}
+
+int smg_dist_info(const smg_handle* h, int64_t* out) {
+  if (!h || !out) return SMG_E_INVALID;
+  out[0] = h->dist.rank;
+  out[1] = h->dist.world;
+  out[2] = h->have_plan ? h->plan.dist_levels : 0;
+  out[3] = h->dist.exchanges;
+  out[4] = h->dist.connected ? 1 : 0;
+  out[5] = static_cast<int64_t>(h->dist.slot_doubles);
+  out[6] = h->dist.exact;
+  out[7] = 0;
+  return SMG_OK;
+}
+
+int smg_dist_level_info(const smg_handle* h, int lv, int64_t* out) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !out) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  const int W = h->dist.world, me = h->dist.rank;
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  out[0] = L.layout;
+  out[1] = L.nparts;
+  out[2] = L.n;
+  out[7] = L.n;
+  if (L.nparts > 1) {
+    int64_t own = 0;
+    for (int i = 0; i < L.n; i++) own += L.part[i] == me;
+    out[2] = own;
+  }
+  if (L.layout == smg::LAYOUT_PARTITIONED) {
+    const std::vector<int>& pp = L.order.phase_ptr;
+    out[6] = pp[static_cast<size_t>(me) * L.n_phases];
+    out[7] = pp[static_cast<size_t>(me + 1) * L.n_phases];
+    for (int q = 0; q < W; q++) {
+      if (q == me) continue;
+      if (!L.halo_u.idx.empty()) {
+        out[3] += static_cast<int64_t>(L.halo_u.idx[static_cast<size_t>(q) * W + me].size());
+        out[4] += static_cast<int64_t>(L.halo_u.idx[static_cast<size_t>(me) * W + q].size());
+      }
+      if (!L.halo_r.idx.empty()) out[5] += static_cast<int64_t>(L.halo_r.idx[static_cast<size_t>(q) * W + me].size());
+    }
+  }
+  return SMG_OK;
+}
+
+int smg_dist_get_part(const smg_handle* h, int lv, int* part_of_row) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !part_of_row) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  for (int i = 0; i < L.n; i++) part_of_row[i] = L.nparts > 1 ? L.part[i] : 0;
+  return SMG_OK;
+}
+
+int smg_dist_get_exchange(const smg_handle* h, int lv, int which, int src, int dst, int* idx, int* n) {
+  SMG_TRY(check_ready(h, false));
+  const int W = h->dist.world;
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !n || src < 0 || dst < 0 || src >= W || dst >= W)
+    return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  const smg::Exchange* X = nullptr;
+  switch (which) {
+    case SMG_X_HALO_U: X = &L.halo_u; break;
+    case SMG_X_HALO_R: X = &L.halo_r; break;
+    case SMG_X_HALO_PU: X = &L.halo_pu; break;
+    case SMG_X_GATHER: X = &L.gather_all; break;
+    default: return SMG_E_INVALID;
+  }
+  if (X->idx.size() != static_cast<size_t>(W) * W) {
+    *n = 0;
+    return SMG_OK;
+  }
+  const std::vector<int>& v = X->idx[static_cast<size_t>(src) * W + dst];
+  *n = static_cast<int>(v.size());
+  if (idx)
+    for (size_t i = 0; i < v.size(); i++) idx[i] = L.order.perm[v[i]];
+  return SMG_OK;
 }
 
 // ---- index / topology outputs ------------------------------------------------------
@@ -1431,8 +1931,8 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
           rc = fail(h, SMG_E_CUDA, "alloc");
           break;
         }
-        smg::launch_residual_norm2(L.sellA.view(), L.b.p, L.u.p, L.n, std::min(k, smg::kMaxK),
-                                   h->norm_scratch.p, h->norm_out.p, h->stream);
+        smg::launch_residual_norm2(own_rows(h, L, L.sellA.view()), L.b.p, L.u.p, L.n,
+                                   std::min(k, smg::kMaxK), h->norm_scratch.p, h->norm_out.p, h->stream);
         h->launches += 2;
         break;
       }
@@ -1487,14 +1987,18 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
   // the traced graph is built with the trace slots baked in and never cached
   SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
   SMG_CUDA(h, h->norm_out.reserve(4));
+  if (dist_on(h)) SMG_CUDA(h, h->dist.normv.reserve(static_cast<size_t>(h->dist.world) * 16));
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK)
     SMG_TRY(prepare_tail(h, 0, h->opt.pre_relax, h->opt.post_relax, k0, std::min(smg::kMaxK, k - k0)));
   smg::trace_start(buf.p, max_events);
   smg::trace_label("norm");
   cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
   if (e == cudaSuccess) {
-    smg::launch_residual_norm2(L0.sellA.view(), L0.b.p, L0.u.p, L0.n, std::min(k, smg::kMaxK),
-                               h->norm_scratch.p, h->norm_out.p, h->stream);
+    const bool part = dist_on(h) && L0.layout == smg::LAYOUT_PARTITIONED;
+    smg::launch_residual_norm2(own_rows(h, L0, L0.sellA.view()), L0.b.p, L0.u.p, L0.n,
+                               std::min(k, smg::kMaxK), h->norm_scratch.p,
+                               part ? h->dist.normv.p + h->dist.rank : h->norm_out.p, h->stream);
+    if (part) exchange(h, h->dist.x_norm, h->dist.normv.p, h->dist.world, 1);
     vcycle_device(h, 0, h->opt.pre_relax, h->opt.post_relax, k);
     e = cudaStreamEndCapture(h->stream, &graph);
   }

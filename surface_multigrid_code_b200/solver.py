@@ -118,6 +118,63 @@ class Solver:
         if rc != L.SMG_OK:
             raise SmgError(rc, self._lib.smg_last_error(self._h).decode())
 
+    # -- multi-GPU (include/smg.h "multi-GPU" block): one Solver per rank ----------------
+    def dist_init(self, rank: int, world: int, comm_bytes: int = 0):
+        self._check(self._lib.smg_dist_init(self._h, int(rank), int(world), int(comm_bytes)))
+        self.rank, self.world = int(rank), int(world)
+        return self
+
+    def dist_handle(self) -> bytes:
+        """This rank's export blob; all-gather the blobs and pass them to dist_connect."""
+        buf = C.create_string_buffer(self._lib.smg_dist_handle_bytes())
+        self._check(self._lib.smg_dist_get_handle(self._h, buf))
+        return buf.raw
+
+    def dist_connect(self, blobs: Sequence[bytes]):
+        raw = b"".join(blobs)
+        self._check(self._lib.smg_dist_connect(self._h, C.create_string_buffer(raw, len(raw))))
+        return self
+
+    def dist_connect_torch(self, group=None):
+        """all-gather the blobs over torch.distributed (any backend) and connect."""
+        import torch.distributed as dist
+
+        blobs = [None] * dist.get_world_size(group)
+        dist.all_gather_object(blobs, self.dist_handle(), group=group)
+        return self.dist_connect(blobs)
+
+    def dist_options(self, exact: bool = False, dist_levels: int = -1, dist_min_rows: int = 0):
+        self._check(self._lib.smg_dist_set_options(self._h, int(bool(exact)), int(dist_levels),
+                                                   int(dist_min_rows)))
+        return self
+
+    def dist_info(self) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.smg_dist_info(self._h, out))
+        keys = ("rank", "world", "dist_levels", "exchanges", "connected", "slot_doubles", "exact")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def dist_level_info(self, lv: int) -> dict:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.smg_dist_level_info(self._h, lv, out))
+        keys = ("layout", "parts", "own_rows", "halo_u_recv", "halo_u_send", "halo_r_recv", "own_begin",
+                "own_end")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def dist_part(self, lv: int) -> np.ndarray:
+        out = np.empty(self.level_rows(lv), dtype=np.int32)
+        self._check(self._lib.smg_dist_get_part(self._h, lv, _ip(out)))
+        return out
+
+    def dist_exchange(self, lv: int, which: str, src: int, dst: int) -> np.ndarray:
+        w = {"halo_u": 0, "halo_r": 1, "halo_pu": 2, "gather": 3}[which]
+        n = C.c_int(0)
+        self._check(self._lib.smg_dist_get_exchange(self._h, lv, w, src, dst, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self._lib.smg_dist_get_exchange(self._h, lv, w, src, dst, _ip(out), C.byref(n)))
+        return out
+
     # -- hierarchy / precompute ----------------------------------------------------
     def set_hierarchy(self, P: Sequence):
         """``P[l-1]`` = ``mg[l].P_full`` (scipy sparse, n_{l-1} x n_l), l = 1..nlev-1."""

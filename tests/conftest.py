@@ -5,6 +5,14 @@ import sys
 import numpy as np
 import pytest
 
+# The multi-GPU tests run several ranks as threads that share one device and one CUDA
+# context.  A kernel spinning in a halo exchange must never sit in front of another rank's
+# kernels in the same hardware work queue, so give the context the maximum number of queues
+# (one process per GPU, the production layout, has no such coupling).  Read at context
+# creation, hence set before anything touches CUDA.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("SMG_XCHG_TIMEOUT_MS", "5000")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
