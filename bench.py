@@ -234,11 +234,30 @@ def run_gpu(args):
 
     pr = build_problem(args.subdiv, args.levels)
     s = Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph)
+    # N > 1: ONE problem, its fine levels partitioned by rows over the N GPUs (halo exchange
+    # through peer-mapped memory inside the V-cycle graph); --replicas: N independent problems
+    partitioned = world > 1 and not args.replicas
+    if partitioned:
+        s.dist_init(rank, world, args.comm_mb << 20)
+        s.dist_options(args.halo, args.dist_levels, args.dist_min_rows)
+        s.dist_connect_torch()
     t0 = time.perf_counter()
     s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
     t_pre = time.perf_counter() - t0
     stats = [s.level_stats(l) for l in range(pr.nlev)]
     n, k = pr.n, pr.k
+    part_info = None
+    own_frac = 1.0
+    if partitioned:
+        li = [s.dist_level_info(l) for l in range(pr.nlev)]
+        own_frac = li[0]["own_rows"] / max(stats[0]["rows"], 1)
+        part_info = {"partitioned_levels": s.dist_info()["dist_levels"],
+                     "halo": {0: "hybrid (exchange per sweep)", 1: "exact (exchange per colour)",
+                              2: "hybrid (exchange per relax call)"}[args.halo],
+                     "rank0_rows_per_level": [x["own_rows"] for x in li],
+                     "rank0_halo_u_rows_per_level": [x["halo_u_recv"] for x in li],
+                     "transport": "peer-mapped device memory (CUDA IPC), stores over NVLink + epoch flags; "
+                                  "no NCCL call on the data path"}
 
     # pinned host buffers for the end-to-end call
     h_rhs = torch.from_numpy(np.ascontiguousarray(pr.rhs)).pin_memory()
@@ -274,9 +293,13 @@ def run_gpu(args):
     time.sleep(1.5)  # nvidia-smi needs about a second before its first sample
     barrier()
     l0 = s.launch_count
+    x0 = s.dist_info()["exchanges"] if partitioned else 0
     ms_iter, _ = s.time_kernel("mg_iteration", 0, k, args.steps, True)
     launches = s.launch_count - l0
     barrier()
+    if part_info is not None:
+        # (exchanges inside a replayed CUDA graph are counted once per capture: see gpu_launches)
+        part_info["exchange_kernels_counted"] = s.dist_info()["exchanges"] - x0
     total_ms = ms_iter * args.steps
 
     # ---- e2e: host-buffer solves ---------------------------------------------------------
@@ -302,11 +325,13 @@ def run_gpu(args):
     kern = {}
     n0, nnz0 = stats[0]["rows"], stats[0]["nnz"]
     n1, p1 = stats[1]["rows"], stats[1]["p_nnz"]
+    # partitioned: a rank streams its own rows only (time includes its halo exchanges)
+    n0, nnz0 = int(n0 * own_frac), int(nnz0 * own_frac)
     for name, nbytes in (("relax_sweep", bytes_gs_sweep(n0, nnz0, k)),
                          ("residual", bytes_residual(n0, nnz0, k)),
                          ("residual_norm", bytes_residual_norm(n0, nnz0, k)),
-                         ("restrict", bytes_restrict(n0, n1, p1, k)),
-                         ("prolong_add", bytes_prolong_add(n0, n1, p1, k))):
+                         ("restrict", bytes_restrict(n0, int(n1 * own_frac), int(p1 * own_frac), k)),
+                         ("prolong_add", bytes_prolong_add(n0, n1, int(p1 * own_frac), k))):
         ms, nl = s.time_kernel(name, 0, k, reps, True)
         kern[name] = {"ms": ms, "launches": nl, "algorithmic_bytes": nbytes,
                       "gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
@@ -365,8 +390,25 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    value = world * args.steps / (total_ms_max * 1e-3)
-    e2e_value = float(c[0]) / (e2e_ms_max * 1e-3)
+    # replicas: every GPU runs its own problem; partitioned: the N GPUs share one
+    jobs = 1 if partitioned else world
+    value = jobs * args.steps / (total_ms_max * 1e-3)
+    e2e_value = float(c[0]) / world * jobs / (e2e_ms_max * 1e-3)
+
+    # the other way to use N GPUs: N independent problems, one per GPU (no exchange at all)
+    replicas = None
+    if partitioned and not args.no_replicas:
+        barrier()
+        with Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph) as s1:
+            s1.set_hierarchy(pr.P).precompute(pr.A, pr.known)
+            s1.time_kernel("mg_iteration", 0, k, 3, True)
+            barrier()
+            ms1, _ = s1.time_kernel("mg_iteration", 0, k, args.steps, True)
+        t1 = torch.tensor([ms1], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+        replicas = {"value": world * 1e3 / float(t1[0]), "unit": UNIT, "scaling": "weak",
+                    "ms_per_step": float(t1[0]),
+                    "what": f"{world} independent copies of the same problem, one per GPU, same timing rules"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -376,31 +418,38 @@ def run_gpu(args):
                "sample": f"{nc} solve-loop iterations (residual norm + V(2,2)) of the same 1M problem, "
                          "oracle/smg_oracle.c single thread (the reference path is single-threaded)",
                "host_cores_available": os.cpu_count()}
+    barrier()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None,
+            "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(pr, args, {
-                "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one problem per GPU)",
+                "parallelism": "single GPU" if world == 1 else (
+                    f"one problem, fine levels row-partitioned over {world} GPUs, coarse levels replicated"
+                    if partitioned else f"{world} independent replicas (one problem per GPU)"),
+                "partition": part_info,
                 "smoother": args.smoother, "cuda_graph": not args.no_graph,
                 "l2": "flushed between timed steps (256 MB write)",
                 "phases_per_level": [st["phases"] for st in stats],
                 "rows_per_level": [st["rows"] for st in stats],
                 "precompute_s": t_pre}),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(8 * (2 * n * k + h_kv.numel())),
-                    "d2h_bytes_per_step": int(8 * n * k + 8 * (cycles_per_solve + 1)),
+                    "h2d_bytes_per_step": int(8 * (2 * n * k + h_kv.numel())) * world,
+                    "d2h_bytes_per_step": int(8 * n * k + 8 * (cycles_per_solve + 1)) * world,
                     "step": f"one smg_solve call = {cycles_per_solve} V-cycles to tol {pr.tol}",
                     "ms_per_solve": e2e_ms_max / n_solves, "solves": n_solves},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "replicas": replicas,
             "final_residual": float(r_his[-1]), "true_residual": true_res,
         }
         print(json.dumps(line), flush=True)
+    barrier()  # nobody frees its comm buffer while a peer may still use it
     s.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -418,6 +467,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-replicas", action="store_true", help="skip the extra replica-mode measurement")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N > 1: N independent problems instead of one row-partitioned problem")
+    ap.add_argument("--halo", type=int, default=0, choices=[0, 1, 2],
+                    help="halo exchange per sweep (0), per colour (1, = single-GPU smoother), per relax call (2)")
+    ap.add_argument("--dist-levels", type=int, default=-1)
+    ap.add_argument("--dist-min-rows", type=int, default=0)
+    ap.add_argument("--comm-mb", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -251,18 +251,20 @@ __device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const
 enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3, MODE_NORM = 4 };
 
 // y = M x | y = b - M x | y += M x | y = M x and z = 0  (z: same shape as y)
+// rows [rb, re); `blk` = index of this CTA among the CTAs of the range
 template <int K, int MODE, bool STAGED>
-__global__ void __launch_bounds__(kBlock)
-sell_apply_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
-                  const int* __restrict__ col, const double* __restrict__ val, const double* x,
-                  int ldx, const double* b, double* y, int ldy, double* z) {
+__device__ __forceinline__ void sell_apply_body(int trace_slot, int rb, int re, int blk, int nslices,
+                                                int max_chunk, const int* __restrict__ slice_ptr,
+                                                const int* __restrict__ col, const double* __restrict__ val,
+                                                const double* x, int ldx, const double* b, double* y,
+                                                int ldy, double* z) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
   pdl_launch_dependents();
-  const int row = (rb & ~31) + blockIdx.x * kBlock + threadIdx.x;
+  const int row = (rb & ~31) + blk * kBlock + threadIdx.x;
   const bool active = row >= rb && row < re;
-  const RowView rv = stage_rows<STAGED>((rb >> 5) + blockIdx.x * kSlices, nslices, row, active, slice_ptr, col,
+  const RowView rv = stage_rows<STAGED>((rb >> 5) + blk * kSlices, nslices, row, active, slice_ptr, col,
                                         val, max_chunk, dyn, &bar);
   pdl_wait();
   stage_wait<STAGED>(&bar);
@@ -284,6 +286,28 @@ sell_apply_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, co
     }
   }
   trace_end(trace_slot);
+}
+
+template <int K, int MODE, bool STAGED>
+__global__ void __launch_bounds__(kBlock)
+sell_apply_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
+                  const int* __restrict__ col, const double* __restrict__ val, const double* x,
+                  int ldx, const double* b, double* y, int ldy, double* z) {
+  sell_apply_body<K, MODE, STAGED>(trace_slot, rb, re, blockIdx.x, nslices, max_chunk, slice_ptr, col, val, x,
+                                   ldx, b, y, ldy, z);
+}
+
+// y = M x on several row ranges in ONE launch (the rows a rank restricts into on the
+// replicated level below a partitioned one are one range per colour)
+template <int K, bool STAGED>
+__global__ void __launch_bounds__(kBlock)
+sell_spmv_ranges_kernel(int trace_slot, RowRanges rr, int nslices, int max_chunk,
+                        const int* __restrict__ slice_ptr, const int* __restrict__ col,
+                        const double* __restrict__ val, const double* x, int ldx, double* y, int ldy) {
+  int j = 0;
+  while (j + 1 < rr.n && (int)blockIdx.x >= rr.blk0[j + 1]) j++;
+  sell_apply_body<K, MODE_SPMV, STAGED>(trace_slot, rr.rb[j], rr.re[j], blockIdx.x - rr.blk0[j], nslices,
+                                        max_chunk, slice_ptr, col, val, x, ldx, nullptr, y, ldy, nullptr);
 }
 
 // Transfer operators have very short rows (a prolongation row holds at most three
@@ -673,16 +697,19 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
 }
 
 // ---- multi-GPU halo exchange (see kernels.hpp::XchgPeer) --------------------------------
-// Grid (ctas per peer, npeers).  Every CTA: (1) pushes its share of the send list into the
-// peer's staging slot with plain stores over NVLink, (2) the last CTA of a peer group to
-// finish publishes the epoch in the peer's flag (release at system scope), (3) waits for
-// the peer's epoch in its own flag, (4) scatters its share of the received values.
-// No CTA waits before it has pushed, so two ranks can never wait for each other; a wait
-// that exceeds the timeout (a peer died) sets ctrl[2] and falls through instead of hanging
-// the GPU.
-// ctrl layout: [2] error flag, [8 + peer] arrival counter, [8 + 64 + peer] exit counter,
+// Low-latency protocol without fences: every value travels as one 16-byte store
+// {value bits, epoch} into the peer's staging slot (a 16-byte aligned vector store is
+// delivered as one unit over NVLink), and the receiver polls each 16-byte word of its own
+// slot until the epoch matches.  A fence + flag protocol costs ~10 us per exchange on
+// B200 (system-scope fences wait for the NVLink round trip); this one costs one store
+// latency.  After the payload every pair of ranks exchanges one extra sync word, so a
+// rank can never run two exchanges ahead of a peer even when a pair has no payload, which
+// is what makes the parity double-buffering of the slots safe.
+// Grid (ctas per peer, npeers); ctrl layout: [2] error flag, [8 + 64 + peer] exit counter,
 // [8 + 128 + peer] epoch of the peer group (advanced by the last CTA of the group to exit,
-// i.e. after every CTA of the group has read it).
+// i.e. after every CTA of the group has read it).  A wait that exceeds the timeout (a peer
+// died) sets ctrl[2] and falls through instead of hanging the GPU; once set, later
+// exchanges do not wait again.
 // late_trigger: release the dependent kernel only after the wait.  Ranks that share one
 // device need it: with the early trigger the whole chain of later kernels of a CUDA graph
 // becomes resident (blocked in griddepcontrol.wait) and can fill the device while the peer
@@ -690,18 +717,16 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
 unsigned long long g_xchg_timeout_ns = 20ull * 1000 * 1000 * 1000;
 constexpr int kXchgMaxPeers = 64;
 
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_ll(double* slot, size_t i, double v, unsigned long long epoch) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2 * i),
+               "l"(__double_as_longlong(v)), "l"(epoch)
+               : "memory");
 }
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ bool ld_ll(const double* slot, size_t i, unsigned long long epoch, double* v) {
+  unsigned long long d, f;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(d), "=l"(f) : "l"(slot + 2 * i) : "memory");
+  *v = __longlong_as_double(d);
+  return f == epoch;
 }
 
 __global__ void __launch_bounds__(kXchgThreads)
@@ -710,51 +735,55 @@ halo_exchange_kernel(int trace_slot, const XchgPeer* __restrict__ peers, double*
   trace_begin(trace_slot);
   if (!late_trigger) pdl_launch_dependents();
   const XchgPeer pr = peers[blockIdx.y];
-  int* arrive = ctrl + 8 + blockIdx.y;
   int* leave = ctrl + 8 + kXchgMaxPeers + blockIdx.y;
   int* group_epoch = ctrl + 8 + 2 * kXchgMaxPeers + blockIdx.y;
   const int nthreads = gridDim.x * kXchgThreads;
+  const int tid = blockIdx.x * kXchgThreads + threadIdx.x;
+  // the send list is immutable: fetch this thread's first index before the dependency wait
+  const int first_idx = tid < pr.n_send ? pr.send_idx[tid] : 0;
   pdl_wait();  // vec is final; the previous exchange kernel has completed
-  const int epoch = ld_acquire_gpu(group_epoch) + 1;
-  const size_t par = (epoch & 1) ? parity_stride : 0;
-  // (1) push
+  const int epoch32 = ld_acquire_gpu(group_epoch) + 1;
+  const unsigned long long epoch = static_cast<unsigned int>(epoch32);
+  const size_t par = (epoch32 & 1) ? parity_stride : 0;
+  // push: payload, then the sync word
   double* dst = pr.remote_slot + par;
   for (int q = 0; q < k; q++)
-    for (int i = blockIdx.x * kXchgThreads + threadIdx.x; i < pr.n_send; i += nthreads)
-      dst[(size_t)q * pr.n_send + i] = ld_vec(vec + pr.send_idx[i] + (size_t)q * ld);
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // (2) publish
-    if (atomicAdd(arrive, 1) == (int)gridDim.x - 1) {
-      atomicExch(arrive, 0);
-      __threadfence_system();
-      st_release_sys(pr.remote_flag, epoch);
+    for (int i = tid; i < pr.n_send; i += nthreads) {
+      const int idx = i == tid ? first_idx : pr.send_idx[i];
+      st_ll(dst, (size_t)q * pr.n_send + i, ld_vec(vec + idx + (size_t)q * ld), epoch);
     }
-    // (3) wait for the peer; once any wait has timed out the context is poisoned and later
-    // exchanges do not wait again
-    const unsigned long long t0 = global_timer();
+  if (tid == 0) st_ll(dst, (size_t)k * pr.n_send, 0.0, epoch);
+  // receive: poll every word of the own slot, scatter
+  const double* src = pr.local_slot + par;
+  const unsigned long long t0 = global_timer();
+  bool dead = false;
+  const int total = k * pr.n_recv + 1;  // + sync word
+  for (int j = tid; j < total; j += nthreads) {
+    double v;
     unsigned spins = 0;
-    while (ld_acquire_sys(pr.local_flag) - epoch < 0) {
+    while (!ld_ll(src, (size_t)j, epoch, &v)) {
+      if (dead) break;
       if ((++spins & 1023u) == 0) {
-        if (ld_acquire_gpu(ctrl + 2) != 0) break;
-        if (global_timer() - t0 > timeout_ns) {
+        if (ld_acquire_gpu(ctrl + 2) != 0 || global_timer() - t0 > timeout_ns) {
           atomicExch(ctrl + 2, 1);
-          break;
+          dead = true;
         }
       }
+    }
+    if (j < total - 1) {
+      const int q = j / pr.n_recv, i = j - q * pr.n_recv;
+      vec[pr.recv_idx[i] + (size_t)q * ld] = v;
     }
   }
   __syncthreads();
   if (late_trigger) pdl_launch_dependents();
-  // (4) scatter
-  const double* src = pr.local_slot + par;
-  for (int q = 0; q < k; q++)
-    for (int i = blockIdx.x * kXchgThreads + threadIdx.x; i < pr.n_recv; i += nthreads)
-      vec[pr.recv_idx[i] + (size_t)q * ld] = ld_relaxed_sys_f64(src + (size_t)q * pr.n_recv + i);
-  if (threadIdx.x == 0 && atomicAdd(leave, 1) == (int)gridDim.x - 1) {
-    atomicExch(leave, 0);
-    st_release_gpu(group_epoch, epoch);
+  if (threadIdx.x == 0) {
+    if (gridDim.x == 1) {
+      st_release_gpu(group_epoch, epoch32);
+    } else if (atomicAdd(leave, 1) == (int)gridDim.x - 1) {
+      atomicExch(leave, 0);
+      st_release_gpu(group_epoch, epoch32);
+    }
   }
   trace_end(trace_slot);
 }
@@ -1003,6 +1032,25 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
 void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
                  int k, cudaStream_t st) {
   launch_apply<MODE_SPMV>(M, use_valT ? M.valT : M.val, x, ldx, nullptr, y, ldy, nullptr, k, st);
+}
+
+void launch_spmv_ranges(const SellDev& M, const RowRanges& ranges, const double* x, int ldx, double* y,
+                        int ldy, int k, cudaStream_t st) {
+  RowRanges rr = ranges;
+  rr.blk0[0] = 0;
+  for (int j = 0; j < rr.n; j++) {
+    const int span = rr.re[j] > rr.rb[j] ? rr.re[j] - (rr.rb[j] & ~31) : 0;
+    rr.blk0[j + 1] = rr.blk0[j] + blocks_for(span, kBlock);
+  }
+  const int g = rr.blk0[rr.n];
+  if (g <= 0) return;
+  if (use_staged(M)) {
+    SMG_DISPATCH_K(k, launch_kernel("spmv_ranges", sell_spmv_ranges_kernel<K, true>, g, kBlock, stage_bytes(M), st,
+                                    rr, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val, x, ldx, y, ldy));
+  } else {
+    SMG_DISPATCH_K(k, launch_kernel("spmv_ranges", sell_spmv_ranges_kernel<K, false>, g, kBlock, 0, st, rr,
+                                    M.nslices, M.max_chunk, M.slice_ptr, M.col, M.val, x, ldx, y, ldy));
+  }
 }
 
 void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, double* z, int ldy,
@@ -1470,11 +1518,12 @@ __global__ void permute_out_kernel(const double* __restrict__ in, const int* __r
 }
 
 __global__ void fill_kernel(int trace_slot, double* p, double v, int64_t n) {
-  (void)trace_slot;
+  trace_begin(trace_slot);
   pdl_launch_dependents();
   pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+  trace_end(trace_slot);
 }
 
 }  // namespace
@@ -1657,6 +1706,8 @@ void preload_k() {
   preload_one(sell_apply_short_kernel<K, MODE_RESIDUAL, 4, 3>);
   preload_one(sell_apply_short_kernel<K, MODE_ADD, 4, 3>);
   preload_one(sell_apply_short_kernel<K, MODE_SPMV_ZERO, 4, 3>);
+  preload_one(sell_spmv_ranges_kernel<K, true>);
+  preload_one(sell_spmv_ranges_kernel<K, false>);
   preload_one(sell_residual_norm_kernel<K, true>);
   preload_one(sell_residual_norm_kernel<K, false>);
   preload_one(sell_gs_phase_kernel<K, true>);

@@ -36,9 +36,20 @@ struct SellDev {
 
 constexpr int kMaxK = 4;  // right-hand sides handled per kernel pass
 
+// up to kMaxRanges row ranges handled by one launch (launch_spmv_ranges)
+constexpr int kMaxRanges = 8;
+struct RowRanges {
+  int n = 0;
+  int rb[kMaxRanges] = {0}, re[kMaxRanges] = {0};
+  int blk0[kMaxRanges + 1] = {0};  // filled by the launcher
+};
+
 // y = M x  (y: nrows x k, ldy; x: ldx)
 void launch_spmv(const SellDev& M, bool use_valT, const double* x, int ldx, double* y, int ldy,
                  int k, cudaStream_t st);
+// y = M x on the rows of `ranges` only, one launch
+void launch_spmv_ranges(const SellDev& M, const RowRanges& ranges, const double* x, int ldx, double* y,
+                        int ldy, int k, cudaStream_t st);
 // y = M x and z = 0 (z has the shape of y): restriction fused with zeroing the coarse guess
 void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, double* z, int ldy,
                       int k, cudaStream_t st);
@@ -116,9 +127,10 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
                      int k, int ps, int pe, const GsFlow& flow, cudaStream_t st);
 
 // ---- multi-GPU halo exchange over peer-mapped memory ------------------------------------
-// One (exchange, peer) pair.  The sender gathers vec[send_idx[i]] into the PEER's staging
-// slot (a store over NVLink), publishes an epoch flag in the peer's memory, waits for the
-// peer's flag in its own memory and scatters its own staging slot into vec[recv_idx[i]].
+// One (exchange, peer) pair.  The sender gathers vec[send_idx[i]] and stores {value, epoch}
+// as one 16-byte word into the PEER's staging slot (a store over NVLink); the receiver polls
+// the words of its own slot until the epoch matches and scatters them into vec[recv_idx[i]].
+// A slot therefore holds (k * n + 1) 16-byte words (the last one is the per-pair sync word).
 // Staging is double-buffered by epoch parity: a rank can be at most one exchange ahead of
 // a peer, because it cannot leave exchange e before the peer has entered it.
 struct XchgPeer {
@@ -127,8 +139,6 @@ struct XchgPeer {
   const int* recv_idx = nullptr;
   double* remote_slot = nullptr;       // peer memory: parity 0; parity 1 at + parity_stride
   const double* local_slot = nullptr;  // own memory, written by the peer
-  int* remote_flag = nullptr;          // peer memory
-  const int* local_flag = nullptr;     // own memory, written by the peer
 };
 constexpr int kXchgThreads = 512;
 // ints of control memory (zero-initialised) an exchange context needs

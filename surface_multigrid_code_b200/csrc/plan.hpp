@@ -168,7 +168,7 @@ struct PlanOptions {
   // rank (always level 0, never the coarsest)
   int world = 1;
   int dist_levels = -1;
-  int dist_min_rows = 100000;
+  int dist_min_rows = 250000;
 };
 
 struct Plan {

@@ -164,7 +164,7 @@ struct LevelDev {
 struct DistCtx {
   int rank = 0, world = 1;
   bool connected = false;
-  int exact = 0;  // 1: halo exchange after every colour (same result as one GPU), 0: per sweep
+  int exact = 0;  // halo exchange after every colour (1: same result as one GPU), sweep (0), relax call (2)
   size_t comm_bytes = 0, flags_bytes = 0, slot_doubles = 0;
   char* comm = nullptr;
   std::vector<char*> peer;    // world entries, peer[rank] == comm
@@ -419,7 +419,7 @@ int build_exchange(smg_handle* h, const smg::Exchange& X, ExchDev* out) {
     out->any = false;
     return SMG_OK;
   }
-  if (X.max_count() * smg::kMaxK > D.slot_doubles)
+  if ((X.max_count() * smg::kMaxK + 1) * 2 > D.slot_doubles)  // 16-byte words, + the sync word
     return fail(h, SMG_E_INVALID,
                 "halo exchange of " + std::to_string(X.max_count()) + " rows does not fit the comm buffer; "
                 "raise smg_dist_init's comm_bytes");
@@ -440,8 +440,6 @@ int build_exchange(smg_handle* h, const smg::Exchange& X, ExchDev* out) {
     // slot s of a rank's staging area holds what rank s sent
     pr.remote_slot = reinterpret_cast<double*>(D.peer[q] + D.flags_bytes) + static_cast<size_t>(me) * D.slot_doubles;
     pr.local_slot = reinterpret_cast<const double*>(D.comm + D.flags_bytes) + static_cast<size_t>(q) * D.slot_doubles;
-    pr.remote_flag = reinterpret_cast<int*>(D.peer[q] + static_cast<size_t>(me) * kFlagStride);
-    pr.local_flag = reinterpret_cast<const int*>(D.comm + static_cast<size_t>(q) * kFlagStride);
     peers.push_back(pr);
   }
   SMG_CUDA(h, out->peers.upload(peers, h->stream));
@@ -579,10 +577,13 @@ void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, i
           h->launches++;
         }
         // exact mode: the rows of this colour reach the other ranks before the next colour
-        if (part && h->dist.exact) exchange(h, L.x_halo_u_phase[p], uu, L.n, kk);
+        if (part && h->dist.exact == 1) exchange(h, L.x_halo_u_phase[p], uu, L.n, kk);
       }
-      // hybrid mode: Gauss-Seidel inside a rank, one halo exchange per sweep across ranks
-      if (part && !h->dist.exact) exchange(h, L.x_halo_u, uu, L.n, kk);
+      // hybrid modes: Gauss-Seidel inside a rank; across ranks one halo exchange per sweep
+      // (0) or per relax call (2: the sweeps of a call see the neighbours' rows as they were
+      // when the call started)
+      if (part && (h->dist.exact == 0 || (h->dist.exact == 2 && it == iters - 1)))
+        exchange(h, L.x_halo_u, uu, L.n, kk);
     }
   }
 }
@@ -634,10 +635,18 @@ void restrict_device(smg_handle* h, int l, const double* x, double* y, int k, do
     const double* xx = x + static_cast<size_t>(k0) * F.n;
     const size_t oc = static_cast<size_t>(k0) * C.n;
     if (part) {
-      for (const auto& rg : C.restrict_ranges) {
-        if (rg.second <= rg.first) continue;
-        smg::launch_spmv(C.sellPT.view().rows(rg.first, rg.second), false, xx, F.n, y + oc, C.n, kk,
-                         h->stream);
+      // one launch for up to kMaxRanges ranges (one per colour on the split level)
+      const auto& rgs = C.restrict_ranges;
+      for (size_t r0 = 0; r0 < rgs.size(); r0 += smg::kMaxRanges) {
+        smg::RowRanges rr;
+        for (size_t r = r0; r < std::min(rgs.size(), r0 + smg::kMaxRanges); r++)
+          if (rgs[r].second > rgs[r].first) {
+            rr.rb[rr.n] = rgs[r].first;
+            rr.re[rr.n] = rgs[r].second;
+            rr.n++;
+          }
+        if (rr.n == 0) continue;
+        smg::launch_spmv_ranges(C.sellPT.view(), rr, xx, F.n, y + oc, C.n, kk, h->stream);
         h->launches++;
       }
       continue;
@@ -1661,7 +1670,8 @@ int smg_dist_connect(smg_handle* h, const void* all_blobs) {
 
 int smg_dist_set_options(smg_handle* h, int exact, int dist_levels, int dist_min_rows) {
   if (!h) return SMG_E_INVALID;
-  h->dist.exact = exact ? 1 : 0;
+  if (exact < 0 || exact > 2) return fail(h, SMG_E_INVALID, "halo mode must be 0, 1 or 2");
+  h->dist.exact = exact;
   h->dist_levels = dist_levels;
   h->dist_min_rows = dist_min_rows;
   if (h->have_plan) drop_graphs_if_device(h);

@@ -143,8 +143,9 @@ class Solver:
         dist.all_gather_object(blobs, self.dist_handle(), group=group)
         return self.dist_connect(blobs)
 
-    def dist_options(self, exact: bool = False, dist_levels: int = -1, dist_min_rows: int = 0):
-        self._check(self._lib.smg_dist_set_options(self._h, int(bool(exact)), int(dist_levels),
+    def dist_options(self, exact=False, dist_levels: int = -1, dist_min_rows: int = 0):
+        """exact: False/0 = halo exchange per sweep, True/1 = per colour, 2 = per relax call."""
+        self._check(self._lib.smg_dist_set_options(self._h, int(exact), int(dist_levels),
                                                    int(dist_min_rows)))
         return self
 

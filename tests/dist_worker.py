@@ -30,6 +30,8 @@ def main():
     pr = mg.sphere_problem(sub, min(4, sub - 1), pad_three=True, tol=1e-10)
     s = Solver(device=dev)
     s.dist_init(rank, world, 64 << 20)
+    halo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    s.dist_options(halo, -1, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     s.dist_connect_torch()
     s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
     z, r_his, ok = s.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 40)
