@@ -82,12 +82,15 @@ __device__ __forceinline__ void trace_begin(int slot) {
 __device__ __forceinline__ void trace_end(int slot) {
   if (slot >= 0 && threadIdx.x == 0) atomicMax(g_trace_buf + 2 * slot + 1, global_timer());
 }
+// per host thread: handles driven by different threads (one rank per thread) label and
+// trace independently
 struct TraceState {
   bool on = false;
   int next = 0, cap = 0;
   std::string label;
   std::vector<std::string> names;
-} g_trace;
+};
+thread_local TraceState g_trace;
 
 template <class... KArgs, class... Args>
 void launch_kernel(const char* name, void (*kernel)(int, KArgs...), int grid, int block, size_t smem,
@@ -731,7 +734,8 @@ __device__ __forceinline__ bool ld_ll(const double* slot, size_t i, unsigned lon
 
 __global__ void __launch_bounds__(kXchgThreads)
 halo_exchange_kernel(int trace_slot, const XchgPeer* __restrict__ peers, double* vec, int ld, int k,
-                     size_t parity_stride, int* ctrl, unsigned long long timeout_ns, int late_trigger) {
+                     size_t parity_stride, int* ctrl, unsigned long long timeout_ns, int late_trigger,
+                     int phases) {
   trace_begin(trace_slot);
   if (!late_trigger) pdl_launch_dependents();
   const XchgPeer pr = peers[blockIdx.y];
@@ -746,13 +750,19 @@ halo_exchange_kernel(int trace_slot, const XchgPeer* __restrict__ peers, double*
   const unsigned long long epoch = static_cast<unsigned int>(epoch32);
   const size_t par = (epoch32 & 1) ? parity_stride : 0;
   // push: payload, then the sync word
-  double* dst = pr.remote_slot + par;
-  for (int q = 0; q < k; q++)
-    for (int i = tid; i < pr.n_send; i += nthreads) {
-      const int idx = i == tid ? first_idx : pr.send_idx[i];
-      st_ll(dst, (size_t)q * pr.n_send + i, ld_vec(vec + idx + (size_t)q * ld), epoch);
-    }
-  if (tid == 0) st_ll(dst, (size_t)k * pr.n_send, 0.0, epoch);
+  if (phases & 1) {
+    double* dst = pr.remote_slot + par;
+    for (int q = 0; q < k; q++)
+      for (int i = tid; i < pr.n_send; i += nthreads) {
+        const int idx = i == tid ? first_idx : pr.send_idx[i];
+        st_ll(dst, (size_t)q * pr.n_send + i, ld_vec(vec + idx + (size_t)q * ld), epoch);
+      }
+    if (tid == 0) st_ll(dst, (size_t)k * pr.n_send, 0.0, epoch);
+  }
+  if (!(phases & 2)) {  // push-only launch (host-synchronised mode): the epoch stays
+    trace_end(trace_slot);
+    return;
+  }
   // receive: poll every word of the own slot, scatter
   const double* src = pr.local_slot + par;
   const unsigned long long t0 = global_timer();
@@ -1109,7 +1119,8 @@ int xchg_ctrl_ints() { return 8 + 3 * kXchgMaxPeers; }
 int xchg_max_peers() { return kXchgMaxPeers; }
 
 void launch_halo_exchange(const XchgPeer* d_peers, int npeers, int ctas_per_peer, double* vec, int ld,
-                          int k, size_t parity_stride, int* ctrl, bool late_trigger, cudaStream_t st) {
+                          int k, size_t parity_stride, int* ctrl, bool late_trigger, int phases,
+                          cudaStream_t st) {
   if (npeers <= 0 || npeers > kXchgMaxPeers) return;
   ctas_per_peer = std::max(1, std::min(ctas_per_peer, 32));
   int slot = -1;
@@ -1127,7 +1138,7 @@ void launch_halo_exchange(const XchgPeer* d_peers, int npeers, int ctas_per_peer
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, halo_exchange_kernel, slot, d_peers, vec, ld, k, parity_stride, ctrl,
-                     g_xchg_timeout_ns, late_trigger ? 1 : 0);
+                     g_xchg_timeout_ns, late_trigger ? 1 : 0, phases);
 }
 
 void launch_gs_phase(const SellDev& M, const double* diag, const double* b, double* u, int ld,

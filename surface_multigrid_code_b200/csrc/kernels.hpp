@@ -147,9 +147,11 @@ int xchg_max_peers();
 // how long an exchange waits for a peer before it gives up and poisons the context (20 s)
 void set_xchg_timeout_ms(long long ms);
 // vec (ld, k columns) is both source and destination; ctrl[2] != 0 after a wait timed out.
-// ctas_per_peer in 1..32 may differ from exchange to exchange.
+// ctas_per_peer in 1..32 may differ from exchange to exchange.  phases: 3 = push and
+// receive in one launch (normal); 1 = push only, 2 = receive only (host-synchronised mode).
 void launch_halo_exchange(const XchgPeer* d_peers, int npeers, int ctas_per_peer, double* vec, int ld,
-                          int k, size_t parity_stride, int* ctrl, bool late_trigger, cudaStream_t st);
+                          int k, size_t parity_stride, int* ctrl, bool late_trigger, int phases,
+                          cudaStream_t st);
 
 // load every solve-time kernel into the current context (see kernels.cu)
 void preload_kernels();

@@ -29,7 +29,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <tuple>
@@ -160,6 +163,8 @@ struct LevelDev {
   std::vector<ExchDev> x_halo_u_phase;
 };
 
+struct HostGroup;
+
 // multi-GPU context: the comm buffer of every rank is mapped into every other rank
 struct DistCtx {
   int rank = 0, world = 1;
@@ -174,9 +179,41 @@ struct DistCtx {
   ExchDev x_norm;
   int64_t exchanges = 0;
   bool shared_device = false;  // some other rank uses this device too (tests): late PDL trigger
+  std::shared_ptr<HostGroup> host_group;  // non-null: host-synchronised exchanges (see HostGroup)
   bool failed = false;  // an exchange timed out: results are garbage, every later call fails
 };
 constexpr size_t kFlagStride = 128;
+
+// Host rendezvous of ranks that live in one process AND share a device (the test layout on a
+// single-GPU box).  Such ranks share hardware queues, copy engines, the allocator and the
+// module loader of one context, and a kernel that spins for a peer can starve exactly the
+// work the peer needs to issue.  They therefore never wait on the device: every exchange is
+// "push kernel, stream sync, host barrier, receive kernel" (no CUDA graphs in this mode).
+// One process per GPU, the production layout, uses the single fused kernel that waits on the
+// device.
+struct HostGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int size = 0, count = 0;
+  long long gen = 0;
+  bool broken = false;
+  bool wait() {  // false: a rank did not arrive within 60 s (or the group is broken)
+    std::unique_lock<std::mutex> lk(m);
+    if (broken) return false;
+    const long long g = gen;
+    if (++count == size) {
+      count = 0;
+      gen++;
+      cv.notify_all();
+      return true;
+    }
+    if (!cv.wait_for(lk, std::chrono::seconds(60), [&] { return gen != g || broken; })) broken = true;
+    if (broken) cv.notify_all();
+    return !broken;
+  }
+};
+std::mutex g_groups_mutex;
+std::map<unsigned long long, std::weak_ptr<HostGroup>> g_groups;
 
 struct DistBlob {  // what smg_dist_get_handle exports (smg_dist_handle_bytes() bytes)
   cudaIpcMemHandle_t ipc;
@@ -515,15 +552,33 @@ int ensure_k(smg_handle* h, int k) {
 }
 
 // ---- multi-GPU helpers ------------------------------------------------------------
+// Ranks that share a device (tests) also share its copy engines, whose queues are FIFO: a
+// copy enqueued behind a kernel that still spins in an exchange would block the copies of
+// the very rank it waits for.  So wait for the stream before enqueuing a copy.
+int drain_if_shared(smg_handle* h) {
+  if (h->dist.shared_device) SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SMG_OK;
+}
+
 // collective: every rank runs the same sequence of exchanges (kernels.hpp::XchgPeer)
 void exchange(smg_handle* h, ExchDev& X, double* vec, int ld, int k) {
   if (!dist_on(h) || !X.any) return;
   DistCtx& D = h->dist;
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
     const int kk = std::min(smg::kMaxK, k - k0);
-    smg::launch_halo_exchange(X.peers.p, D.world - 1, X.ctas, vec + static_cast<size_t>(k0) * ld, ld,
-                              kk, D.slot_doubles * D.world, D.ctrl.p, D.shared_device, h->stream);
-    h->launches++;
+    double* v = vec + static_cast<size_t>(k0) * ld;
+    const size_t stride = D.slot_doubles * D.world;
+    if (D.host_group) {
+      smg::launch_halo_exchange(X.peers.p, D.world - 1, X.ctas, v, ld, kk, stride, D.ctrl.p, true, 1, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (!D.host_group->wait()) D.failed = true;  // reported by check_exchange
+      smg::launch_halo_exchange(X.peers.p, D.world - 1, X.ctas, v, ld, kk, stride, D.ctrl.p, true, 2, h->stream);
+      h->launches += 2;
+    } else {
+      smg::launch_halo_exchange(X.peers.p, D.world - 1, X.ctas, v, ld, kk, stride, D.ctrl.p, D.shared_device,
+                                3, h->stream);
+      h->launches++;
+    }
     D.exchanges++;
   }
 }
@@ -791,6 +846,7 @@ int residual_norm_device(smg_handle* h, int l, const double* b, const double* u,
   if (part) {
     // every rank adds the same partial sums in rank order: identical residuals everywhere
     int* xflag = reinterpret_cast<int*>(h->h_norm + 48);
+    SMG_TRY(drain_if_shared(h));
     SMG_CUDA(h, cudaMemcpyAsync(h->h_norm + 64, D.normv.p, sizeof(double) * nchunks * D.world,
                                 cudaMemcpyDeviceToHost, h->stream));
     SMG_CUDA(h, cudaMemcpyAsync(xflag, D.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1044,8 +1100,10 @@ int set_device(smg_handle* h) {
 // an exchange wait that timed out (a peer rank died or never made the matching call)
 int check_exchange(smg_handle* h) {
   if (!dist_on(h)) return SMG_OK;
+  if (h->dist.failed) return fail(h, SMG_E_INTERNAL, "halo exchange: a peer rank did not reach the host rendezvous");
   int* flag = reinterpret_cast<int*>(h->h_norm + 48);
   *flag = 0;
+  SMG_TRY(drain_if_shared(h));
   SMG_CUDA(h, cudaMemcpyAsync(flag, h->dist.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
   if (*flag) {
@@ -1074,6 +1132,7 @@ int stage_out(smg_handle* h, int l, const double* src, DevBuf<double>& stage, do
   if (cnt == 0) return SMG_OK;
   smg::launch_permute_out(src, L.perm.p, stage.p, L.n, k, h->stream);
   h->launches++;
+  SMG_TRY(drain_if_shared(h));
   SMG_CUDA(h, cudaMemcpyAsync(host, stage.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
   SMG_TRY(check_exchange(h));
@@ -1664,6 +1723,26 @@ int smg_dist_connect(smg_handle* h, const void* all_blobs) {
       D.opened[q] = 1;
     }
   }
+  // every rank in this process and some device shared: host-synchronised exchanges
+  bool same_process = true;
+  unsigned long long key = 0;
+  for (int q = 0; q < D.world; q++) {
+    DistBlob b;
+    std::memcpy(&b, static_cast<const char*>(all_blobs) + static_cast<size_t>(q) * sizeof(DistBlob), sizeof(b));
+    same_process = same_process && b.pid == me;
+    if (q == 0) key = b.ptr;
+  }
+  if (same_process && D.shared_device) {
+    std::lock_guard<std::mutex> lk(g_groups_mutex);
+    std::shared_ptr<HostGroup> g = g_groups[key].lock();
+    if (!g) {
+      g = std::make_shared<HostGroup>();
+      g->size = D.world;
+      g_groups[key] = g;
+    }
+    D.host_group = g;
+    h->opt.use_graph = 0;
+  }
   D.connected = true;
   return SMG_OK;
 }
@@ -1981,6 +2060,7 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
   SMG_TRY(check_ready(h, true));
   if (!names || !t0_us || !t1_us || !n_events || k < 1 || max_events < 1)
     return fail(h, SMG_E_INVALID, "bad argument");
+  if (h->dist.host_group) return fail(h, SMG_E_UNSUPPORTED, "no CUDA graphs when ranks share a device");
   SMG_TRY(set_device(h));
   SMG_TRY(ensure_k(h, k));
   DevBuf<unsigned long long> buf;
@@ -2024,6 +2104,7 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
     cudaGraphLaunch(exec, h->stream);
   }
   std::vector<unsigned long long> out(init.size());
+  drain_if_shared(h);
   cudaMemcpyAsync(out.data(), buf.p, out.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                   h->stream);
   e = cudaStreamSynchronize(h->stream);

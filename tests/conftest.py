@@ -35,9 +35,29 @@ def _ensure_built():
         g.build()
 
 
+def _warm_up_gpu():
+    """First CUDA use on a fresh box pages in cuSOLVER/cuBLAS (can take a minute): do it once,
+    outside any test's own time limits."""
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return
+    except Exception:
+        return
+    from surface_multigrid_code_b200 import meshgen as mg
+    from surface_multigrid_code_b200.solver import Solver
+
+    pr = mg.sphere_problem(3, 2, pad_three=True)
+    with Solver(device=0) as s:
+        s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
+        s.solve(pr.rhs, pr.z0, pr.known_val, 1e-8, 5)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def built():
     _ensure_built()
+    _warm_up_gpu()
 
 
 @pytest.fixture(scope="session")

@@ -1,7 +1,7 @@
-"""Ranks that share a device also share its context: cusolver / allocator calls that
-synchronise the whole device (precompute) must not run while another rank already spins in
-an exchange, so test bodies call ``s.barrier()`` between precompute and the first collective
-operator.  With one process per GPU no such care is needed.
+"""Ranks that share a device also share its context (hardware queues, copy engines,
+allocator, module loader); the library detects that layout and synchronises their exchanges on
+the host instead of spinning on the device (csrc/smg.cu::HostGroup).  Test bodies still call
+``s.barrier()`` between precompute and the first collective operator to keep the ranks close.
 
 Drive N ranks of the row-partitioned solver from one process: one thread per rank
 (ctypes releases the GIL inside libsmg calls, so the ranks really run concurrently, which
@@ -12,7 +12,7 @@ from surface_multigrid_code_b200.solver import Solver
 
 
 def run_ranks(world, fn, devices=None, smoother="multicolour", exact=False, dist_levels=-1,
-              min_rows=0, timeout=60.0, comm_bytes=32 << 20, **solver_kw):
+              min_rows=0, timeout=300.0, comm_bytes=32 << 20, **solver_kw):
     """fn(rank, solver) -> result, called on `world` connected solvers; returns the list of
     results in rank order.  Raises the first exception of any rank (or on timeout)."""
     devices = devices or [0] * world
