@@ -36,15 +36,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "V-cycles/sec (1M-vertex sphere Poisson, 5-level V(2,2), FP64)"
+METRIC = "V-cycles/sec (1M-vertex sphere Poisson, 5-level V(2,2), FP64)"  # the default workload
+
+
+def metric_name(pr):
+    if pr.n == 1048578 and pr.nlev == 5:
+        return METRIC
+    return f"V-cycles/sec ({pr.n}-vertex sphere Poisson, {pr.nlev}-level V(2,2), FP64)"
+
 UNIT = "V-cycles/s"
 FALLBACK_HBM_GBS = 6650.0
 
 
-def build_problem(n_sub: int, n_levels: int):
+def build_problem(n_sub: int, n_levels: int, max_iter: int = 20):
     from surface_multigrid_code_b200 import meshgen as mg
 
-    return mg.sphere_problem(n_sub, n_levels, tol=1e-10, max_iter=20, pad_three=True)
+    return mg.sphere_problem(n_sub, n_levels, tol=1e-10, max_iter=max_iter, pad_three=True)
 
 
 def workload_config(pr, args, extra=None):
@@ -190,13 +197,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pr = build_problem(args.subdiv, args.levels)
+    pr = build_problem(args.subdiv, args.levels, args.max_iter)
     times = cpu_iterations(pr, args.warmup, args.steps)
     total = sum(times)
     v = args.steps / total
     line = {
         "impl": "reference",
-        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric_name(pr), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(pr, args, {"parallelism": "host cpu, 1 thread"}),
@@ -232,13 +239,16 @@ def run_gpu(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    pr = build_problem(args.subdiv, args.levels)
+    pr = build_problem(args.subdiv, args.levels, args.max_iter)
     s = Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph)
     # N > 1: ONE problem, its fine levels partitioned by rows over the N GPUs (halo exchange
     # through peer-mapped memory inside the V-cycle graph); --replicas: N independent problems
     partitioned = world > 1 and not args.replicas
     if partitioned:
-        s.dist_init(rank, world, args.comm_mb << 20)
+        # staging: every rank receives up to n/world rows x 4 columns as 16-byte words from
+        # every peer, double-buffered
+        comm_mb = args.comm_mb or max(256, (pr.n * 4 * 16 * 2 * 5 // 4 >> 20) + 16)
+        s.dist_init(rank, world, comm_mb << 20)
         s.dist_options(args.halo, args.dist_levels, args.dist_min_rows)
         s.dist_connect_torch()
     t0 = time.perf_counter()
@@ -421,7 +431,7 @@ def run_gpu(args):
     barrier()
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(pr), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None,
             "dtype": "f64",
@@ -463,6 +473,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--subdiv", type=int, default=9, help="octahedron subdivisions (9 = 1M vertices)")
     ap.add_argument("--levels", type=int, default=5)
+    ap.add_argument("--max-iter", type=int, default=20,
+                    help="maxIter of the solve (reference default 20; the 4M sphere needs ~24 cycles for 1e-10)")
     ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "wavefront"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -474,7 +486,7 @@ def main():
                     help="halo exchange per sweep (0), per colour (1, = single-GPU smoother), per relax call (2)")
     ap.add_argument("--dist-levels", type=int, default=-1)
     ap.add_argument("--dist-min-rows", type=int, default=0)
-    ap.add_argument("--comm-mb", type=int, default=256)
+    ap.add_argument("--comm-mb", type=int, default=0, help="peer-mapped staging buffer per GPU (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
