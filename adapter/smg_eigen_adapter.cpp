@@ -28,6 +28,8 @@
 #include <smg.h>
 
 #include <cstdlib>
+#include <unistd.h>
+
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -83,8 +85,32 @@ void precompute_impl(const Eigen::SparseMatrix<double>& A_in, const Eigen::Vecto
   if (const char* s = std::getenv("SMG_SMOOTHER")) opt.smoother = std::atoi(s);
   opt.verbose = env_flag("SMG_QUIET") ? 0 : 1;
   smg_handle* raw = nullptr;
+  // Multi-GPU: launch the unmodified example once per GPU (mpirun -np N, srun, a shell loop);
+  // every process runs the same main.cpp on the same mesh.  Rank / world come from SMG_RANK /
+  // SMG_WORLD or the launcher's own variables, the device defaults to the rank, and the ranks
+  // find each other through files in SMG_RENDEZVOUS_DIR (include/smg.h, multi-GPU block).
+  int rank = 0, world = 1;
+  for (const char* name : {"SMG_WORLD", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE"})
+    if (const char* s = std::getenv(name)) { world = std::atoi(s); break; }
+  for (const char* name : {"SMG_RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "RANK"})
+    if (const char* s = std::getenv(name)) { rank = std::atoi(s); break; }
+  if (world > 1 && !std::getenv("SMG_DEVICE")) opt.device = rank;
+  if (const char* s = std::getenv("SMG_DEVICE")) opt.device = std::atoi(s);
   check(nullptr, smg_create(&raw, &opt), "smg_create");
   std::shared_ptr<smg_handle> h(raw, HandleDeleter());
+  if (world > 1) {
+    static int round = 0;  // one rendezvous per precompute call, same order on every rank
+    const char* dir = std::getenv("SMG_RENDEZVOUS_DIR");
+    // unique per job: stale files of an earlier run must never be read (SMG_JOB_ID, else the
+    // launcher's pid, which all ranks started by one mpirun / torchrun share)
+    const char* job = std::getenv("SMG_JOB_ID");
+    const std::string tag = "smg_" + (job ? std::string(job) : std::to_string(static_cast<long long>(getppid()))) +
+                            "_" + std::to_string(round++);
+    check(h.get(), smg_dist_init(h.get(), rank, world, 0), "smg_dist_init");
+    if (const char* s = std::getenv("SMG_HALO")) check(h.get(), smg_dist_set_options(h.get(), std::atoi(s), -1, 0), "smg_dist_set_options");
+    check(h.get(), smg_dist_connect_files(h.get(), dir ? dir : "/dev/shm", tag.c_str(), 120000),
+          "smg_dist_connect_files");
+  }
 
   // hierarchy as mg_precompute left it (src/mg_precompute.cpp:71-77): mg[lv].P_full
   const int nlev = static_cast<int>(mg.size());

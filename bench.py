@@ -368,10 +368,11 @@ def run_gpu(args):
     except Exception as e:  # profiling aid only
         in_situ = {"error": str(e)}
     clk = clocks.stop()
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("relax_sweep_dram_bytes")
+            tj = json.load(fh)
+        traffic, traffic_note = tj.get("relax_sweep_dram_bytes"), tj.get("note")
     except Exception:
         pass
     gs = kern["relax_sweep"]
@@ -381,6 +382,7 @@ def run_gpu(args):
         "bound": "hbm", "kernel": "sell_gs_phase_kernel (fine-level Gauss-Seidel, "
                                   f"{gs['launches']} colour launches per sweep)",
         "achieved": pre_gbs, "peak": peak, "unit": "GB/s", "frac": pre_gbs / peak, "traffic": traffic,
+        "traffic_note": traffic_note,
         "peak_source": peak_src, "algorithmic_bytes_per_sweep": gs["algorithmic_bytes"],
         "ms_per_sweep": ms_pre / pre_sweeps,
         "how": f"{pre_sweeps} pre-smoothing sweeps back to back as inside a V-cycle, CUDA events on the "

@@ -182,6 +182,15 @@ int smg_dist_get_handle(smg_handle *h, void *blob);
 /* all_blobs: world blobs in rank order.  Buffers of ranks living in the same process are
  * used directly (peer access), others are opened with cudaIpcOpenMemHandle. */
 int smg_dist_connect(smg_handle *h, const void *all_blobs);
+/* Host-side helper for callers without MPI / torch.distributed: all-gather `bytes` bytes per
+ * rank through files in `dir`, a directory every rank of the node can see (e.g.
+ * /dev/shm/<job>); `tag` distinguishes rendezvous rounds inside one directory.  Rank r writes
+ * dir/tag.r (temp file + rename), then polls for the other world-1 files.  Returns
+ * SMG_E_INTERNAL after timeout_ms.  No CUDA involved. */
+int smg_rendezvous_files(const char *dir, const char *tag, int rank, int world, const void *mine,
+                         size_t bytes, void *all, int timeout_ms);
+/* smg_dist_get_handle + smg_rendezvous_files + smg_dist_connect in one call */
+int smg_dist_connect_files(smg_handle *h, const char *dir, const char *tag, int timeout_ms);
 /* exact = 1: halo exchange after every colour (the N-rank smoother is then the same
  * multicolour Gauss-Seidel as on one GPU); 0 (default): one exchange per sweep (Gauss-Seidel
  * inside a rank, Jacobi coupling across ranks); 2: one exchange per relax call (the sweeps of

@@ -95,6 +95,8 @@ SIGNATURES = {
     "smg_dist_handle_bytes": (C.c_int, []),
     "smg_dist_get_handle": (C.c_int, [_vp, _vp]),
     "smg_dist_connect": (C.c_int, [_vp, _vp]),
+    "smg_rendezvous_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, _vp, C.c_size_t, _vp, C.c_int]),
+    "smg_dist_connect_files": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_int]),
     "smg_dist_set_options": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "smg_dist_info": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "smg_dist_level_info": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),

@@ -1747,6 +1747,54 @@ int smg_dist_connect(smg_handle* h, const void* all_blobs) {
   return SMG_OK;
 }
 
+int smg_rendezvous_files(const char* dir, const char* tag, int rank, int world, const void* mine,
+                         size_t bytes, void* all, int timeout_ms) {
+  if (!dir || !tag || !mine || !all || world < 1 || rank < 0 || rank >= world || bytes == 0)
+    return SMG_E_INVALID;
+  const std::string base = std::string(dir) + "/" + tag + ".";
+  {  // publish: write to a private name, then rename (atomic within a file system)
+    const std::string tmp = base + std::to_string(rank) + ".tmp." + std::to_string(static_cast<long long>(getpid()));
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return SMG_E_INVALID;
+    const size_t w = std::fwrite(mine, 1, bytes, f);
+    if (std::fclose(f) != 0 || w != bytes) return SMG_E_INVALID;
+    if (std::rename(tmp.c_str(), (base + std::to_string(rank)).c_str()) != 0) return SMG_E_INVALID;
+  }
+  const double t0 = now_ms();
+  std::vector<char> have(static_cast<size_t>(world), 0);
+  int missing = world;
+  while (missing > 0) {
+    for (int q = 0; q < world; q++) {
+      if (have[q]) continue;
+      FILE* f = std::fopen((base + std::to_string(q)).c_str(), "rb");
+      if (!f) continue;
+      const size_t r = std::fread(static_cast<char*>(all) + static_cast<size_t>(q) * bytes, 1, bytes, f);
+      std::fclose(f);
+      if (r == bytes) {
+        have[q] = 1;
+        missing--;
+      }
+    }
+    if (missing > 0) {
+      if (timeout_ms >= 0 && now_ms() - t0 > timeout_ms) return SMG_E_INTERNAL;
+      usleep(2000);
+    }
+  }
+  return SMG_OK;
+}
+
+int smg_dist_connect_files(smg_handle* h, const char* dir, const char* tag, int timeout_ms) {
+  if (!h) return SMG_E_INVALID;
+  if (h->dist.world == 1) return SMG_OK;
+  DistBlob mine;
+  SMG_TRY(smg_dist_get_handle(h, &mine));
+  std::vector<DistBlob> all(static_cast<size_t>(h->dist.world));
+  const int rc = smg_rendezvous_files(dir, tag, h->dist.rank, h->dist.world, &mine, sizeof(mine), all.data(),
+                                      timeout_ms);
+  if (rc != SMG_OK) return fail(h, rc, std::string("file rendezvous in ") + (dir ? dir : "(null)") + " failed");
+  return smg_dist_connect(h, all.data());
+}
+
 int smg_dist_set_options(smg_handle* h, int exact, int dist_levels, int dist_min_rows) {
   if (!h) return SMG_E_INVALID;
   if (exact < 0 || exact > 2) return fail(h, SMG_E_INVALID, "halo mode must be 0, 1 or 2");

@@ -143,6 +143,12 @@ class Solver:
         dist.all_gather_object(blobs, self.dist_handle(), group=group)
         return self.dist_connect(blobs)
 
+    def dist_connect_files(self, directory: str, tag: str = "smg", timeout_ms: int = 60000):
+        """all-gather the blobs through files in `directory` (no MPI / torch needed) and connect."""
+        self._check(self._lib.smg_dist_connect_files(self._h, directory.encode(), tag.encode(),
+                                                     int(timeout_ms)))
+        return self
+
     def dist_options(self, exact=False, dist_levels: int = -1, dist_min_rows: int = 0):
         """exact: False/0 = halo exchange per sweep, True/1 = per colour, 2 = per relax call."""
         self._check(self._lib.smg_dist_set_options(self._h, int(exact), int(dist_levels),

@@ -127,3 +127,33 @@ def test_hierarchy_validation(problems):
         Solver(device="none").set_hierarchy(pr.P).precompute(pr.A[:-1][:, :-1], None)
     with pytest.raises(SmgError):
         Solver(device="none").precompute(pr.A, pr.known)  # no hierarchy yet
+
+
+def test_file_rendezvous_all_gathers_blobs(tmp_path):
+    """smg_rendezvous_files (include/smg.h): the launcher-free way for N processes of the
+    reference's examples to exchange their export blobs.  Ranks = threads here."""
+    import ctypes as C
+    import threading
+
+    lib = _lib.load()
+    world, nbytes = 4, 96
+    mine = [bytes([r]) * nbytes for r in range(world)]
+    got = [None] * world
+    rcs = [None] * world
+
+    def body(r):
+        out = C.create_string_buffer(world * nbytes)
+        rcs[r] = lib.smg_rendezvous_files(str(tmp_path).encode(), b"t0", r, world, mine[r], nbytes, out, 20000)
+        got[r] = out.raw
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert rcs == [0] * world
+    assert all(g == b"".join(mine) for g in got)
+    # a rank that never shows up: timeout, not a hang
+    out = C.create_string_buffer(2 * nbytes)
+    assert lib.smg_rendezvous_files(str(tmp_path).encode(), b"t1", 0, 2, mine[0], nbytes, out, 200) == 10
+    assert lib.smg_rendezvous_files(b"/nonexistent-dir", b"t", 0, 2, mine[0], nbytes, out, 200) == 1
