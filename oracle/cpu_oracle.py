@@ -1,9 +1,15 @@
-"""ctypes front end of the CPU oracle (``oracle/smg_oracle.c``).
+"""ctypes front end of the CPU oracle (``oracle/smg_oracle.c``) and, with ``impl="ref"``, of
+``oracle/_ref/libsmg_ref.so``: the reference's own two hot-path source files compiled
+unmodified against the Eigen stand-in of ``oracle/ref_shim`` (``make -C oracle ref``).  Both
+libraries export the same ``orc_*`` entry points.
 
 TEST INFRASTRUCTURE ONLY.  Importable from ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs; the product package
-``surface_multigrid_code_b200`` never imports it.  PARITY UNPINNED (see the C file's
-header): the reference has no golden vectors for this path and cannot be built here.
+``surface_multigrid_code_b200`` never imports it.  Pinning: the reference has no golden
+vectors for this path and genuine Eigen is not in this image, so the C restatement is pinned
+against (a) the reference sources on the stand-in Eigen (``tests/test_reference_sources.py``)
+and (b) an independent scipy restatement; what remains unpinned is Eigen 3.3.7's own
+arithmetic order, restated from its sources in ``oracle/ref_shim/Eigen/Sparse``.
 """
 from __future__ import annotations
 
@@ -16,7 +22,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsmg_oracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libsmg_ref.so")
 _lib = None
+_ref_lib = None
 
 _ip = C.POINTER(C.c_int)
 _dp = C.POINTER(C.c_double)
@@ -29,12 +37,16 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
-        L = C.CDLL(_LIB_PATH)
+def ref_available(build_if_possible: bool = True) -> bool:
+    """oracle/_ref/libsmg_ref.so exists (it is built where /root/reference is mounted and
+    travels to the GPU box as a built file)."""
+    if not os.path.exists(_REF_PATH) and build_if_possible and os.path.isdir("/root/reference/src"):
+        subprocess.call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return os.path.exists(_REF_PATH)
+
+
+def _declare(L):
+    if True:
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -54,7 +66,22 @@ def lib():
         L.orc_matrix_copy.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp]
         L.orc_get_diag.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_coarse_bandwidth.argtypes = [C.c_void_p]
-        _lib = L
+    return L
+
+
+def lib(impl: str = "port"):
+    """impl: "port" = oracle/smg_oracle.c, "ref" = the reference sources on the Eigen stand-in."""
+    global _lib, _ref_lib
+    if impl == "ref":
+        if _ref_lib is None:
+            if not ref_available():
+                raise OSError("oracle/_ref/libsmg_ref.so is not built (make -C oracle ref needs /root/reference)")
+            _ref_lib = _declare(C.CDLL(_REF_PATH))
+        return _ref_lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = _declare(C.CDLL(_LIB_PATH))
     return _lib
 
 
@@ -87,9 +114,10 @@ def _from_colmajor(buf, n, k, ndim):
 class Oracle:
     """CPU restatement of min_quad_with_fixed_mg_{precompute,solve} + mg_VCycle."""
 
-    def __init__(self, P: List):
+    def __init__(self, P: List, impl: str = "port"):
         self.nlev = len(P) + 1
-        self._L = lib()
+        self.impl = impl
+        self._L = lib(impl)
         self._h = C.c_void_p(self._L.orc_create(self.nlev))
         for l, p in enumerate(P, start=1):
             p = p.tocsc()

@@ -1,0 +1,1 @@
+// igl/diag.h -- included by the reference headers, nothing of it is used on the hot path (test infrastructure shim)

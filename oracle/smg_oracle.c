@@ -9,12 +9,15 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * library (libsmg.so) never links or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path
- * and cannot be compiled in this image (it needs Eigen 3.3.7, which libigl's
- * CMake downloads: libigl/cmake/LibiglDownloadExternal.cmake:67-74; no Eigen on
- * disk, no network).  The oracle is therefore pinned only against an
- * independent scipy restatement (tests/test_oracle.py) and libigl's adjacent
- * known-answer tests for the problem generator.
+ * PINNING: the reference ships no tests / golden vectors for this path and genuine
+ * Eigen 3.3.7 is not in this image (libigl's CMake downloads it:
+ * libigl/cmake/LibiglDownloadExternal.cmake:67-74; no network).  This restatement is
+ * pinned against (a) the reference's OWN two source files compiled unmodified on an
+ * Eigen stand-in (oracle/_ref, `make ref`; tests/test_reference_sources.py: index
+ * outputs, Galerkin values, relax / A / restrict / prolong bit-exact), (b) an
+ * independent scipy restatement (tests/test_oracle.py) and (c) libigl's adjacent
+ * known-answer tests for the problem generator.  Still unpinned: Eigen's own
+ * arithmetic order, which both this file and the stand-in restate.
  *
  * Third-party arithmetic restated here (Eigen 3.3.7, not vendored in the
  * reference):
