@@ -10,9 +10,12 @@
 // this file, `-I<repo>/include`, link `-lsmg`.
 //
 // Host code stays C++/Eigen as the reference's; Eigen 3.3.7 is NOT available in the image
-// this repository is developed in, so this file is compile-checked there only against
-// a declaration-level Eigen stub (tests/eigen_stub); it has not been linked against the
-// real Eigen yet (stated in DESIGN.md).
+// this repository is developed in, so there this file is compiled, linked and RUN against the
+// functional Eigen stand-in of oracle/ref_shim: the headless 03 example (examples/) and the
+// drop-in test tests/test_gpu_adapter_dropin.py, which drives the reference's own sources and
+// this file through one identical harness.  It has not been linked against genuine Eigen yet
+// (stated in DESIGN.md); it only uses data() / rows() / cols() / resize() and the raw CSC
+// pointers of SparseMatrix, which have the same meaning there.
 //
 // Semantics kept (reference file:line):
 //   * precompute mutates `data` (n, known, unknown) and `mg` is left untouched unless

@@ -6,9 +6,9 @@
 // The viewer, mesh IO and mg_precompute (CPU hierarchy build, out of scope) are replaced by
 // a flat problem file written by surface_multigrid_code_b200/meshgen.py::write_problem_file:
 // it holds what main.cpp has in hand before the two solver calls (A, mg[lv].P_full, b, B,
-// bval, z0).  Build (the image has no Eigen, so tests use tests/eigen_stub; with real
+// bval, z0).  Build (the image has no Eigen, so tests use oracle/ref_shim; with real
 // Eigen 3.3.7 drop the first -I):
-//   g++ -std=c++17 -I tests/eigen_stub -I /root/reference/src -I include
+//   g++ -std=c++17 -I oracle/ref_shim -I /root/reference/src -I include
 //       examples/03_mg_solver_headless.cpp adapter/smg_eigen_adapter.cpp
 //       surface_multigrid_code_b200/libsmg.so -Wl,-rpath,$PWD/surface_multigrid_code_b200 -o 03_headless
 //   ./03_headless problem.bin [tolerance [maxIter]]

@@ -23,6 +23,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsmg_oracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libsmg_ref.so")
+# the same orc_* entry points over adapter/smg_eigen_adapter.cpp + libsmg.so (GPU): the drop-in
+# under test, reachable here only so that tests can drive it exactly like the reference code
+_ADAPTER_PATH = os.path.join(_HERE, "_ref", "libsmg_adapter.so")
+_adapter_lib = None
 _lib = None
 _ref_lib = None
 
@@ -43,6 +47,10 @@ def ref_available(build_if_possible: bool = True) -> bool:
     if not os.path.exists(_REF_PATH) and build_if_possible and os.path.isdir("/root/reference/src"):
         subprocess.call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return os.path.exists(_REF_PATH)
+
+
+def adapter_available() -> bool:
+    return ref_available() and os.path.exists(_ADAPTER_PATH)
 
 
 def _declare(L):
@@ -71,7 +79,13 @@ def _declare(L):
 
 def lib(impl: str = "port"):
     """impl: "port" = oracle/smg_oracle.c, "ref" = the reference sources on the Eigen stand-in."""
-    global _lib, _ref_lib
+    global _lib, _ref_lib, _adapter_lib
+    if impl == "adapter":
+        if _adapter_lib is None:
+            if not (ref_available() and os.path.exists(_ADAPTER_PATH)):
+                raise OSError("oracle/_ref/libsmg_adapter.so is not built (make -C oracle ref)")
+            _adapter_lib = _declare(C.CDLL(_ADAPTER_PATH))
+        return _adapter_lib
     if impl == "ref":
         if _ref_lib is None:
             if not ref_available():

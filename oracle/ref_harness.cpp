@@ -13,10 +13,23 @@
 // optimising build inlines most of those instantiations away, so a separately compiled harness
 // could not link against them.  Including them makes every template visible here; the files
 // themselves are byte-for-byte the reference's.
+//
+// -DSMG_HARNESS_USE_ADAPTER builds the SAME entry points over adapter/smg_eigen_adapter.cpp
+// instead (the drop-in replacement of those two files, which forwards to libsmg.so on the
+// GPU): tests/test_gpu_adapter_dropin.py then drives one identical call sequence through the
+// reference's code and through the drop-in and compares what comes back.
+#ifdef SMG_HARNESS_USE_ADAPTER
+#include <smg_eigen_adapter.cpp>
+
+#include <cstdlib>
+#else
 #include <mg_VCycle.cpp>
 #include <min_quad_with_fixed_mg.cpp>
+#endif
 
+#include <cstdio>
 #include <cstring>
+#include <exception>
 #include <iostream>
 #include <sstream>
 #include <vector>
@@ -61,6 +74,15 @@ void to_colmajor(const M& m, double* out) {
   if (m.size() > 0) std::memcpy(out, m.data(), sizeof(double) * static_cast<size_t>(m.size()));
 }
 
+// the drop-in reports failures (no CUDA device, ...) as exceptions: never let one cross the C ABI
+#define ORC_TRY try {
+#define ORC_CATCH(ret)                                        \
+  }                                                           \
+  catch (const std::exception& e) {                           \
+    std::fprintf(stderr, "ref_harness: %s\n", e.what());      \
+    ret;                                                      \
+  }
+
 // the reference prints one line per iteration (min_quad_with_fixed_mg.cpp:111,334,349)
 struct Quiet {
   std::ostringstream sink;  // constructed before `old` takes its buffer
@@ -73,6 +95,10 @@ struct Quiet {
 extern "C" {
 
 void* orc_create(int nlev) {
+#ifdef SMG_HARNESS_USE_ADAPTER
+  setenv("SMG_MIRROR_TO_HOST", "1", 1);  // mg[lv].A / A_diag / P / PT, data.LHS / Auk come back
+  setenv("SMG_QUIET", "1", 1);
+#endif
   Ref* s = new Ref();
   s->nlev = nlev;
   s->mg.resize(static_cast<size_t>(nlev));
@@ -96,6 +122,7 @@ int orc_set_prolongation(void* h, int lv, int rows, int cols, const int* colptr,
 // min_quad_with_fixed_mg_precompute, both variants (src/min_quad_with_fixed_mg.cpp:3-51, :137-257)
 int orc_precompute(void* h, int n, const int* colptr, const int* rowidx, const double* val,
                    const int* known, int nknown) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   if (s->nlev < 2) return -2;
   for (size_t lv = 1; lv < s->mg.size(); lv++) {  // a fresh mg_precompute state
@@ -117,59 +144,76 @@ int orc_precompute(void* h, int n, const int* colptr, const int* rowidx, const d
     for (int i = 0; i < nknown; i++) kn(i) = known[i];
     min_quad_with_fixed_mg_precompute(A, kn, s->data, s->mg, s->solver);
   }
+#ifdef SMG_HARNESS_USE_ADAPTER
+  return 0;  // the drop-in ignores the caller's SimplicialLDLT (coarse factorisation on the device)
+#else
   return s->solver.ok() ? 0 : -3;
+#endif
+  ORC_CATCH(return -4)
 }
 
 // relax (src/mg_VCycle.cpp:113-178)
 void orc_relax(void* h, int lv, int iters, const double* B, double* u, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   const Eigen::Index n = s->mg[static_cast<size_t>(lv)].A.rows();
   Eigen::MatrixXd b = from_colmajor(B, n, k), x = from_colmajor(u, n, k);
   relax(b, lv, iters, x, s->mg);
   to_colmajor(x, u);
+  ORC_CATCH(return)
 }
 
 // A (src/mg_VCycle.cpp:62-70)
 void orc_apply_A(void* h, int lv, const double* u, double* Au, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   Eigen::MatrixXd x = from_colmajor(u, s->mg[static_cast<size_t>(lv)].A.cols(), k), y;
   A(x, s->mg, lv, y);
   to_colmajor(y, Au);
+  ORC_CATCH(return)
 }
 
 // restrict (src/mg_VCycle.cpp:72-81)
 void orc_restrict(void* h, int lv, const double* xin, double* Rx, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   Eigen::MatrixXd x = from_colmajor(xin, s->mg[static_cast<size_t>(lv) + 1].PT.cols(), k), y;
   restrict(x, s->mg, lv, y);
   to_colmajor(y, Rx);
+  ORC_CATCH(return)
 }
 
 // prolong (src/mg_VCycle.cpp:83-92)
 void orc_prolong(void* h, int lv, const double* xin, double* Px, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   Eigen::MatrixXd x = from_colmajor(xin, s->mg[static_cast<size_t>(lv) + 1].P.cols(), k), y;
   prolong(x, s->mg, lv, y);
   to_colmajor(y, Px);
+  ORC_CATCH(return)
 }
 
 // coarseSolve (src/mg_VCycle.cpp:181-201)
 void orc_coarse_solve(void* h, const double* B, double* u, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   const int lv = s->nlev - 1;
   const Eigen::Index n = s->mg[static_cast<size_t>(lv)].A.rows();
   Eigen::MatrixXd b = from_colmajor(B, n, k), x = from_colmajor(u, n, k);
   coarseSolve(s->solver, b, lv, x, s->mg);
   to_colmajor(x, u);
+  ORC_CATCH(return)
 }
 
 // mg_VCycle (src/mg_VCycle.cpp:3-59)
 void orc_vcycle(void* h, const double* B, int pre, int post, int lv, double* u, int k) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   const Eigen::Index n = s->mg[static_cast<size_t>(lv)].A.rows();
   Eigen::MatrixXd b = from_colmajor(B, n, k), x = from_colmajor(u, n, k);
   mg_VCycle(s->solver, b, pre, post, lv, x, s->mg);
   to_colmajor(x, u);
+  ORC_CATCH(return)
 }
 
 // min_quad_with_fixed_mg_solve with explicit tolerance and maxIter
@@ -177,6 +221,7 @@ void orc_vcycle(void* h, const double* B, int pre, int post, int lv, double* u, 
 // VectorXd instantiation like 03/04, k > 1 through the MatrixXd one like 05
 int orc_solve(void* h, const double* RHS, const double* known_val, const double* z0, int k, double tol,
               int max_iter, double* z, double* r_his, int* n_his) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   const Eigen::Index n = s->data.n;
   std::vector<double> hist;
@@ -204,11 +249,13 @@ int orc_solve(void* h, const double* RHS, const double* known_val, const double*
   for (size_t i = 0; i < hist.size(); i++) r_his[i] = hist[i];
   *n_his = static_cast<int>(hist.size());
   return ok ? 1 : 0;
+  ORC_CATCH(return -4)
 }
 
 // `cycles` iterations of the solve loop on the unknown-sized system (the body of
 // src/min_quad_with_fixed_mg.cpp:330-347 without the early exit): timing aid
 void orc_iterate(void* h, const double* bu, double* zu, int k, int cycles, double* r_his) {
+  ORC_TRY
   Ref* s = static_cast<Ref*>(h);
   const Eigen::Index nu = s->mg[0].A.rows();
   Eigen::MatrixXd b = from_colmajor(bu, nu, k), x = from_colmajor(zu, nu, k);
@@ -217,6 +264,7 @@ void orc_iterate(void* h, const double* bu, double* zu, int k, int cycles, doubl
     mg_VCycle(s->solver, b, 2, 2, 0, x, s->mg);
   }
   to_colmajor(x, zu);
+  ORC_CATCH(return)
 }
 
 int orc_num_levels(void* h) { return static_cast<Ref*>(h)->nlev; }
@@ -264,6 +312,10 @@ void orc_get_diag(void* h, int lv, double* out) {
 }
 int orc_coarse_bandwidth(void*) { return -1; }
 const char* orc_impl(void) {
+#ifdef SMG_HARNESS_USE_ADAPTER
+  return "adapter/smg_eigen_adapter.cpp + libsmg.so behind the reference's headers (ref_shim Eigen stand-in)";
+#else
   return "reference sources (mg_VCycle.cpp, min_quad_with_fixed_mg.cpp) on the ref_shim Eigen stand-in";
+#endif
 }
 }  // extern "C"

@@ -57,7 +57,7 @@ def test_multicolour_solves_real_meshes(name):
 def test_reference_facing_cpp_boundary(tmp_path):
     """The reference's own call sequence (03_mg_solver/main.cpp:66-75) compiled against the
     reference's unmodified headers + adapter/smg_eigen_adapter.cpp + libsmg.so (Eigen replaced
-    by tests/eigen_stub; built by __graft_entry__.build() where /root/reference is mounted)."""
+    by oracle/ref_shim; built by __graft_entry__.build() where /root/reference is mounted)."""
     import os
     import subprocess
 
