@@ -2,13 +2,50 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "../../include/smg.h"
 
 namespace smg {
+
+namespace {
+// SMG_PLAN_TIMING=1: stage times of build_plan on stderr
+struct StageTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  StageTimer() : on(std::getenv("SMG_PLAN_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "plan: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
+// fn(begin, end) over [0, n) in contiguous chunks on up to 8 host threads (SMG_PLAN_THREADS);
+// every use below writes disjoint output ranges, so results do not depend on the thread count
+template <class Fn>
+void parallel_chunks(int64_t n, int64_t min_per_thread, Fn fn) {
+  static const int max_threads = [] {
+    int t = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* e = std::getenv("SMG_PLAN_THREADS")) t = std::atoi(e);
+    return std::max(1, std::min(t, 8));
+  }();
+  const int nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(max_threads, n / std::max<int64_t>(1, min_per_thread))));
+  if (nt <= 1) {
+    fn(static_cast<int64_t>(0), n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back([=] { fn(n * t / nt, n * (t + 1) / nt); });
+  for (auto& x : th) x.join();
+}
+}  // namespace
 
 std::vector<int> setdiff_range(int n, const int* known, int nknown) {
   std::vector<char> mark(static_cast<size_t>(n) + 1, 0);
@@ -102,24 +139,57 @@ Csc spgemm_pattern(const Csc& L, const Csc& R) {
   Y.rows = L.rows;
   Y.cols = R.cols;
   Y.colptr.assign(static_cast<size_t>(R.cols) + 1, 0);
-  std::vector<int> mask(static_cast<size_t>(L.rows), -1);
-  std::vector<int> touched;
-  Y.rowidx.reserve(static_cast<size_t>(R.nnz()) * 2);
-  for (int j = 0; j < R.cols; j++) {
-    touched.clear();
-    for (int p = R.colptr[j]; p < R.colptr[j + 1]; p++) {
-      const int k = R.rowidx[p];
-      for (int q = L.colptr[k]; q < L.colptr[k + 1]; q++) {
-        const int i = L.rowidx[q];
-        if (mask[i] != j) {
-          mask[i] = j;
-          touched.push_back(i);
+  // columns of the product are independent: every thread computes a contiguous range of
+  // them into its own buffer, the buffers are concatenated in column order
+  struct Part {
+    int64_t c0 = 0, c1 = 0;
+    std::vector<int> rows, cnt;
+  };
+  std::vector<Part> parts(8);
+  std::vector<char> used(8, 0);
+  std::mutex mu;
+  int next_part = 0;
+  parallel_chunks(R.cols, 4096, [&](int64_t c0, int64_t c1) {
+    int id;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      id = next_part++;
+    }
+    Part& P = parts[static_cast<size_t>(id)];
+    used[static_cast<size_t>(id)] = 1;
+    P.c0 = c0;
+    P.c1 = c1;
+    P.cnt.assign(static_cast<size_t>(c1 - c0), 0);
+    std::vector<int> mask(static_cast<size_t>(L.rows), -1);
+    std::vector<int> touched;
+    for (int64_t j = c0; j < c1; j++) {
+      touched.clear();
+      for (int p = R.colptr[j]; p < R.colptr[j + 1]; p++) {
+        const int k = R.rowidx[p];
+        for (int q = L.colptr[k]; q < L.colptr[k + 1]; q++) {
+          const int i = L.rowidx[q];
+          if (mask[i] != static_cast<int>(j)) {
+            mask[i] = static_cast<int>(j);
+            touched.push_back(i);
+          }
         }
       }
+      std::sort(touched.begin(), touched.end());
+      P.rows.insert(P.rows.end(), touched.begin(), touched.end());
+      P.cnt[static_cast<size_t>(j - c0)] = static_cast<int>(touched.size());
     }
-    std::sort(touched.begin(), touched.end());
-    Y.rowidx.insert(Y.rowidx.end(), touched.begin(), touched.end());
-    Y.colptr[j + 1] = static_cast<int>(Y.rowidx.size());
+  });
+  std::vector<const Part*> ord;
+  for (size_t i = 0; i < parts.size(); i++)
+    if (used[i]) ord.push_back(&parts[i]);
+  std::sort(ord.begin(), ord.end(), [](const Part* a, const Part* b) { return a->c0 < b->c0; });
+  size_t total = 0;
+  for (const Part* P : ord) total += P->rows.size();
+  Y.rowidx.reserve(total);
+  for (const Part* P : ord) {
+    for (int64_t j = P->c0; j < P->c1; j++)
+      Y.colptr[static_cast<size_t>(j) + 1] = Y.colptr[static_cast<size_t>(j)] + P->cnt[static_cast<size_t>(j - P->c0)];
+    Y.rowidx.insert(Y.rowidx.end(), P->rows.begin(), P->rows.end());
   }
   return Y;
 }
@@ -285,14 +355,20 @@ Sell build_sell(const Csc& X, const std::vector<int>& row_perm,
   S.nrows = n;
   S.nslices = (n + kSliceRows - 1) / kSliceRows;
   S.slice_ptr.assign(static_cast<size_t>(S.nslices) + 1, 0);
-  for (int s = 0; s < S.nslices; s++) {
-    int w = 0;
-    const int r1 = std::min(n, (s + 1) * kSliceRows);
-    for (int r = s * kSliceRows; r < r1; r++) {
-      const int c = row_perm[r];
-      w = std::max(w, X.colptr[c + 1] - X.colptr[c]);
+  std::vector<int> width(static_cast<size_t>(S.nslices), 0);
+  parallel_chunks(S.nslices, 2048, [&](int64_t s0, int64_t s1) {
+    for (int64_t s = s0; s < s1; s++) {
+      int w = 0;
+      const int r1 = static_cast<int>(std::min<int64_t>(n, (s + 1) * kSliceRows));
+      for (int r = static_cast<int>(s) * kSliceRows; r < r1; r++) {
+        const int c = row_perm[r];
+        w = std::max(w, X.colptr[c + 1] - X.colptr[c]);
+      }
+      width[static_cast<size_t>(s)] = w;
     }
-    const int64_t nxt = static_cast<int64_t>(S.slice_ptr[s]) + static_cast<int64_t>(w) * kSliceRows;
+  });
+  for (int s = 0; s < S.nslices; s++) {
+    const int64_t nxt = static_cast<int64_t>(S.slice_ptr[s]) + static_cast<int64_t>(width[s]) * kSliceRows;
     if (nxt > INT32_MAX) {
       S.nrows = -1;  // signals overflow to the caller
       return S;
@@ -302,30 +378,32 @@ Sell build_sell(const Csc& X, const std::vector<int>& row_perm,
   const int64_t tot = S.slice_ptr[S.nslices];
   S.col.assign(tot, 0);
   S.src.assign(tot, -1);
-  std::vector<std::pair<int, int>> ent;
-  for (int s = 0; s < S.nslices; s++) {
-    const int base = S.slice_ptr[s];
-    const int w = (S.slice_ptr[s + 1] - base) / kSliceRows;
-    for (int lane = 0; lane < kSliceRows; lane++) {
-      const int r = s * kSliceRows + lane;
-      int j = 0;
-      int last_col = (r < n) ? 0 : 0;
-      if (r < n) {
-        const int c = row_perm[r];
-        ent.clear();
-        for (int p = X.colptr[c]; p < X.colptr[c + 1]; p++) ent.emplace_back(col_iperm[X.rowidx[p]], p);
-        if (sort_cols) std::sort(ent.begin(), ent.end());
-        for (const auto& e : ent) {
-          last_col = e.first;
-          S.col[base + j * kSliceRows + lane] = e.first;
-          S.src[base + j * kSliceRows + lane] = e.second;
-          j++;
+  parallel_chunks(S.nslices, 2048, [&](int64_t s0, int64_t s1) {
+    std::vector<std::pair<int, int>> ent;
+    for (int64_t s = s0; s < s1; s++) {
+      const int base = S.slice_ptr[s];
+      const int w = (S.slice_ptr[s + 1] - base) / kSliceRows;
+      for (int lane = 0; lane < kSliceRows; lane++) {
+        const int r = static_cast<int>(s) * kSliceRows + lane;
+        int j = 0;
+        int last_col = 0;
+        if (r < n) {
+          const int c = row_perm[r];
+          ent.clear();
+          for (int p = X.colptr[c]; p < X.colptr[c + 1]; p++) ent.emplace_back(col_iperm[X.rowidx[p]], p);
+          if (sort_cols) std::sort(ent.begin(), ent.end());
+          for (const auto& e : ent) {
+            last_col = e.first;
+            S.col[base + j * kSliceRows + lane] = e.first;
+            S.src[base + j * kSliceRows + lane] = e.second;
+            j++;
+          }
         }
+        // padding: zero value, column = last real column of the row (same sector)
+        for (; j < w; j++) S.col[base + j * kSliceRows + lane] = last_col;
       }
-      // padding: zero value, column = last real column of the row (same sector)
-      for (; j < w; j++) S.col[base + j * kSliceRows + lane] = last_col;
     }
-  }
+  });
   return S;
 }
 
@@ -368,6 +446,7 @@ static void remap_src(Sell& S, const std::vector<int>& map) {
 }
 
 static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
+  StageTimer st;
   const int n = L.A.cols;
   L.n = n;
   L.a_col = entry_columns(L.A);
@@ -375,6 +454,7 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
   for (int j = 0; j < n; j++)
     for (int p = L.A.colptr[j]; p < L.A.colptr[j + 1]; p++)
       if (L.A.rowidx[p] == j) L.diag_pos[j] = p;
+  st.lap("  columns, diag positions");
   const Csc& A = L.Alive;  // layout decisions look at the compute pattern only
   std::vector<int> order;
   if (opt.locality_reorder) {
@@ -383,6 +463,7 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
     order.resize(n);
     std::iota(order.begin(), order.end(), 0);
   }
+  st.lap("  bfs order");
   std::vector<int> rank(n);
   for (int t = 0; t < n; t++) rank[order[t]] = t;
   if (opt.smoother == SMG_SMOOTHER_WAVEFRONT) {
@@ -391,6 +472,7 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
     L.phase = greedy_colours(A, order, &L.n_phases);
   }
   if (n == 0) L.n_phases = 0;
+  st.lap("  phases (colouring)");
   if (L.nparts > 1 && L.layout != LAYOUT_PLAIN) {
     // multi-GPU: group rows by (part, phase) or (phase, part); see LevelPlan::group
     if (L.layout == LAYOUT_PARTITIONED && L.part.empty()) {
@@ -410,8 +492,10 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
   L.layout = LAYOUT_PLAIN;
   L.nparts = 1;
   L.order = make_row_order(A, L.phase, L.n_phases, rank, opt.sigma);
+  st.lap("  row order");
   L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
   remap_src(L.sellA, L.live_src);
+  st.lap("  build SELL A");
   // block dependency ranges for the dataflow smoother
   const int np = L.n_phases;
   L.blk_ofs.assign(static_cast<size_t>(np) + 1, 0);
@@ -423,7 +507,7 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
     L.blk_ofs[p + 1] = L.blk_ofs[p] + nb;
   }
   const int nblk = L.blk_ofs[np];
-  if (np <= 16) {
+  if (np <= 16 && opt.dataflow) {
     L.dep_lo.assign(static_cast<size_t>(nblk) * np, 1);
     L.dep_hi.assign(static_cast<size_t>(nblk) * np, 0);
     for (int r = 0; r < n; r++) {  // r: permuted row
@@ -575,6 +659,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
       pl.error = "prolongation sizes do not chain";
       return SMG_E_INVALID;
     }
+  StageTimer stage;
   pl.n = A.rows;
   pl.lv.resize(nlev);
   Csc Apat = A;
@@ -632,6 +717,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
     }
     for (int l = 1; l < nlev; l++) pl.lv[l].PT = transpose(pl.lv[l].P, nullptr);  // :226
   }
+  stage.lap("slices, pruning, transposes");
   // patterns of the Galerkin products, :223-228 (left to right: (PT*A)*P)
   pl.lv[0].A = pl.LHS;
   for (int l = 1; l < nlev; l++) {
@@ -643,6 +729,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
     pl.lv[l].t1_col = entry_columns(pl.lv[l].T1);
     pl.lv[l].A = spgemm_pattern(pl.lv[l].T1, pl.lv[l].P);
   }
+  stage.lap("Galerkin patterns");
   // compute patterns (LevelPlan::Alive): Galerkin patterns of the zero-free part of P
   std::vector<Csc> Pz(nlev), PTz(nlev);
   std::vector<std::vector<int>> pz_src(nlev), ptz_src(nlev);
@@ -656,6 +743,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
     pl.lv[l].Alive = spgemm_pattern(Tz, Pz[l]);
     pl.lv[l].live_src = locate_entries(pl.lv[l].A, pl.lv[l].Alive);
   }
+  stage.lap("compute patterns");
   // multi-GPU: which levels are partitioned by rows
   pl.world = std::max(1, opt.world);
   pl.dist_levels = 0;
@@ -692,6 +780,7 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
         return SMG_E_INVALID;
       }
   }
+  stage.lap("level layouts (order, SELL A)");
   for (int l = 1; l < nlev; l++) {
     LevelPlan& L = pl.lv[l];
     // y_fine = P x_coarse : rows of P = columns of PT's CSC (explicit zeros skipped)
@@ -705,7 +794,9 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
       return SMG_E_UNSUPPORTED;
     }
   }
+  stage.lap("SELL P / PT");
   if (pl.world > 1) plan_exchanges(pl, Pz);
+  stage.lap("exchange lists");
   return SMG_OK;
 }
 

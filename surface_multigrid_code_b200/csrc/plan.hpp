@@ -163,6 +163,7 @@ struct PlanOptions {
   int locality_reorder = 1;
   int sigma = 256;
   int sort_cols = -1;  // -1: on for multicolour, off for wavefront (bit-parity order)
+  int dataflow = 0;    // 1: also plan the block dependency ranges of the dataflow smoother
   // multi-GPU: number of ranks the fine levels are partitioned over, and how many levels
   // (from level 0) are partitioned; < 0: every level with at least dist_min_rows rows per
   // rank (always level 0, never the coarsest)

@@ -1424,6 +1424,7 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   po.smoother = h->opt.smoother;
   po.locality_reorder = h->opt.locality_reorder;
   po.sigma = h->opt.sigma > 0 ? h->opt.sigma : 1;
+  po.dataflow = h->opt.dataflow || h->plan_only;  // (plan-only handles report the schedule statistics)
   po.world = h->dist.world;
   po.dist_levels = h->dist_levels;
   if (h->dist_min_rows > 0) po.dist_min_rows = h->dist_min_rows;
