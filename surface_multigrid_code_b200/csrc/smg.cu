@@ -182,7 +182,7 @@ struct DistCtx {
   std::shared_ptr<HostGroup> host_group;  // non-null: host-synchronised exchanges (see HostGroup)
   bool failed = false;  // an exchange timed out: results are garbage, every later call fails
 };
-constexpr size_t kFlagStride = 128;
+constexpr size_t kFlagStride = 128;  // header region of the comm buffer: one line per rank (reserved)
 
 // Host rendezvous of ranks that live in one process AND share a device (the test layout on a
 // single-GPU box).  Such ranks share hardware queues, copy engines, the allocator and the
