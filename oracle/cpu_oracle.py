@@ -142,6 +142,10 @@ class Oracle:
             assert rc == 0
         self.n = None
 
+    def refresh_count(self) -> int:
+        """precompute calls served by a numeric-only refresh (adapter build of the harness only)"""
+        return int(self._L.orc_refresh_count()) if hasattr(self._L, "orc_refresh_count") else 0
+
     def __del__(self):
         try:
             if self._h:

@@ -311,6 +311,14 @@ void orc_get_diag(void* h, int lv, double* out) {
   to_colmajor(s->mg[static_cast<size_t>(lv)].A_diag, out);
 }
 int orc_coarse_bandwidth(void*) { return -1; }
+// precompute calls the drop-in served by a numeric-only refresh (0 for the reference sources)
+int orc_refresh_count(void) {
+#ifdef SMG_HARNESS_USE_ADAPTER
+  return smg_adapter_refresh_count();
+#else
+  return 0;
+#endif
+}
 const char* orc_impl(void) {
 #ifdef SMG_HARNESS_USE_ADAPTER
   return "adapter/smg_eigen_adapter.cpp + libsmg.so behind the reference's headers (ref_shim Eigen stand-in)";

@@ -92,3 +92,32 @@ def test_adapter_default_smoother_reaches_the_reference_solution(problems, name,
     z2, r2, ok2 = ref.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 40)
     assert ok1 and ok2 and abs(len(r1) - len(r2)) <= 2
     assert np.linalg.norm(z1 - z2) <= 1e-7 * np.linalg.norm(z2)
+
+
+def test_repeated_precompute_with_new_values_is_a_numeric_refresh(problems, smoother_env):
+    """05_example_mean_curvature_flow/main.cpp:74 calls min_quad_with_fixed_mg_precompute every
+    time step with the same pattern and new values: the drop-in reuses its plan
+    (smg_update_values) and still returns what the reference's code returns."""
+    import scipy.sparse as sp
+
+    pr = problems["mcf"]
+    smoother_env(0)
+    ref = Oracle(pr.P, impl="ref").precompute(pr.A, pr.known)
+    ada = Oracle(pr.P, impl="adapter").precompute(pr.A, pr.known)
+    before = ada.refresh_count()
+    A2 = (pr.A + 0.37 * sp.identity(pr.A.shape[0], format="csc")).tocsc()
+    A2.sort_indices()
+    assert np.array_equal(A2.indptr, pr.A.tocsc().indptr)  # same pattern, new values
+    ref.precompute(A2, pr.known)
+    ada.precompute(A2, pr.known)
+    assert ada.refresh_count() == before + 1
+    for lv in range(pr.nlev):
+        assert _same_matrix(ada.matrix(lv, "A"), ref.matrix(lv, "A")), lv
+        assert np.array_equal(ada.diag(lv), ref.diag(lv)), lv
+    z1, r1, ok1 = ada.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 30)
+    z2, r2, ok2 = ref.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 30)
+    assert ok1 == ok2 and len(r1) == len(r2)
+    assert np.linalg.norm(z1 - z2) <= 1e-9 * np.linalg.norm(z2)
+    # a different pattern on the same objects is a full precompute again
+    pr2 = problems["sphere_pad"]
+    assert pr2.A.shape != pr.A.shape
