@@ -118,6 +118,13 @@ def test_repeated_precompute_with_new_values_is_a_numeric_refresh(problems, smoo
     z2, r2, ok2 = ref.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 30)
     assert ok1 == ok2 and len(r1) == len(r2)
     assert np.linalg.norm(z1 - z2) <= 1e-9 * np.linalg.norm(z2)
-    # a different pattern on the same objects is a full precompute again
-    pr2 = problems["sphere_pad"]
-    assert pr2.A.shape != pr.A.shape
+    # SMG_NO_REFRESH=1 forces the full precompute; same results
+    os.environ["SMG_NO_REFRESH"] = "1"
+    try:
+        ada.precompute(pr.A, pr.known)
+    finally:
+        os.environ.pop("SMG_NO_REFRESH", None)
+    assert ada.refresh_count() == before + 1
+    ref.precompute(pr.A, pr.known)
+    for lv in range(pr.nlev):
+        assert _same_matrix(ada.matrix(lv, "A"), ref.matrix(lv, "A")), lv
