@@ -10,64 +10,62 @@
 #include <vector>
 
 namespace igl {
-// Y = X(R, C), sparse (slice.cpp:13-77): every stored entry of X, in storage order, goes to
-// every (i, j) with R(i) == row and C(j) == col; setFromTriplets sorts and sums duplicates.
+// Y = X(R, C), sparse.  Semantics of libigl's overload (slice.cpp:13-77): every stored entry
+// X(r, c) - explicit zeros included - lands on every output position (i, j) with R(i) == r and
+// C(j) == c; duplicates created by repeated indices are summed and every output column is sorted
+// (that is what its setFromTriplets call does).  Implemented here with bucketed index lists.
 template <typename TX, typename TY, typename DerivedR, typename DerivedC>
 inline void slice(const Eigen::SparseMatrix<TX>& X, const Eigen::DenseBase<DerivedR>& R,
                   const Eigen::DenseBase<DerivedC>& C, Eigen::SparseMatrix<TY>& Y) {
-  const int xm = static_cast<int>(X.rows()), xn = static_cast<int>(X.cols());
-  const int ym = static_cast<int>(R.size()), yn = static_cast<int>(C.size());
-  if (ym == 0 || yn == 0) {
-    Y.resize(ym, yn);
-    return;
+  const Eigen::Index out_rows = R.size(), out_cols = C.size();
+  Y.resize(out_rows, out_cols);
+  if (out_rows == 0 || out_cols == 0) return;
+  // targets_of_row[r] = output rows that read input row r, as one flat list with offsets
+  std::vector<int> row_ofs(static_cast<size_t>(X.rows()) + 1, 0), row_tgt(static_cast<size_t>(out_rows));
+  for (Eigen::Index i = 0; i < out_rows; i++) row_ofs[static_cast<size_t>(R(i)) + 1]++;
+  for (size_t r = 0; r + 1 < row_ofs.size(); r++) row_ofs[r + 1] += row_ofs[r];
+  {
+    std::vector<int> fill(row_ofs.begin(), row_ofs.end() - 1);
+    for (Eigen::Index i = 0; i < out_rows; i++) row_tgt[static_cast<size_t>(fill[static_cast<size_t>(R(i))]++)] = static_cast<int>(i);
   }
-  std::vector<std::vector<int>> RI(static_cast<size_t>(xm)), CI(static_cast<size_t>(xn));
-  for (int i = 0; i < ym; i++) RI[static_cast<size_t>(R(i))].push_back(i);
-  for (int i = 0; i < yn; i++) CI[static_cast<size_t>(C(i))].push_back(i);
-  std::vector<Eigen::Triplet<TY>> entries;
-  for (int k = 0; k < X.outerSize(); ++k)
-    for (typename Eigen::SparseMatrix<TX>::InnerIterator it(X, k); it; ++it)
-      for (int r : RI[static_cast<size_t>(it.row())])
-        for (int c : CI[static_cast<size_t>(it.col())]) entries.emplace_back(r, c, it.value());
-  Y.resize(ym, yn);
-  Y.setFromTriplets(entries.begin(), entries.end());
+  std::vector<Eigen::Triplet<TY>> trip;
+  for (Eigen::Index j = 0; j < out_cols; j++) {
+    const Eigen::Index src_col = C(j);
+    for (typename Eigen::SparseMatrix<TX>::InnerIterator e(X, src_col); e; ++e)
+      for (int t = row_ofs[static_cast<size_t>(e.row())]; t < row_ofs[static_cast<size_t>(e.row()) + 1]; t++)
+        trip.emplace_back(row_tgt[static_cast<size_t>(t)], static_cast<int>(j), static_cast<TY>(e.value()));
+  }
+  Y.setFromTriplets(trip.begin(), trip.end());
 }
 
 // Y = X(R, C), dense (slice.cpp:115-153)
 template <typename DerivedX, typename DerivedR, typename DerivedC, typename DerivedY>
 inline void slice(const Eigen::DenseBase<DerivedX>& X, const Eigen::DenseBase<DerivedR>& R,
                   const Eigen::DenseBase<DerivedC>& C, Eigen::PlainObjectBase<DerivedY>& Y) {
-  const int ym = static_cast<int>(R.size()), yn = static_cast<int>(C.size());
-  if (ym == 0 || yn == 0) {
-    Y.resize(ym, yn);
-    return;
-  }
-  Y.resize(ym, yn);
-  for (int i = 0; i < ym; i++)
-    for (int j = 0; j < yn; j++) Y(i, j) = X(R(i), C(j));
+  Y.resize(R.size(), C.size());
+  for (Eigen::Index j = 0; j < C.size(); j++)
+    for (Eigen::Index i = 0; i < R.size(); i++) Y(i, j) = X(R(i), C(j));
 }
 
-// Y = X(R, :) (dim 1) or X(:, R) (dim 2), sparse or dense (slice.cpp:79-113)
+// Y = X(R, :) for dim == 1, X(:, R) for dim == 2; sparse or dense (slice.cpp:79-113)
 template <typename MatX, typename DerivedR, typename MatY>
 inline void slice(const MatX& X, const Eigen::DenseBase<DerivedR>& R, const int dim, MatY& Y) {
-  Eigen::Matrix<typename DerivedR::Scalar, Eigen::Dynamic, 1> C;
-  switch (dim) {
-    case 1:
-      if (X.cols() == 0) {
-        Y.resize(R.size(), 0);
-        return;
-      }
-      C = Eigen::Matrix<typename DerivedR::Scalar, Eigen::Dynamic, 1>::LinSpaced(X.cols(), 0, static_cast<typename DerivedR::Scalar>(X.cols() - 1));
-      return slice(X, R, C, Y);
-    case 2:
-      if (X.rows() == 0) {
-        Y.resize(0, R.size());
-        return;
-      }
-      C = Eigen::Matrix<typename DerivedR::Scalar, Eigen::Dynamic, 1>::LinSpaced(X.rows(), 0, static_cast<typename DerivedR::Scalar>(X.rows() - 1));
-      return slice(X, C, R, Y);
-    default:
+  typedef Eigen::Matrix<typename DerivedR::Scalar, Eigen::Dynamic, 1> IndexVector;
+  typedef typename DerivedR::Scalar I;
+  if (dim == 1) {
+    if (X.cols() == 0) {
+      Y.resize(R.size(), 0);
       return;
+    }
+    const IndexVector all = IndexVector::LinSpaced(X.cols(), I(0), static_cast<I>(X.cols() - 1));
+    slice(X, R, all, Y);
+  } else if (dim == 2) {
+    if (X.rows() == 0) {
+      Y.resize(0, R.size());
+      return;
+    }
+    const IndexVector all = IndexVector::LinSpaced(X.rows(), I(0), static_cast<I>(X.rows() - 1));
+    slice(X, all, R, Y);
   }
 }
 }  // namespace igl

@@ -5,31 +5,25 @@
 #include <Eigen/Core>
 
 namespace igl {
-// Y(R(i), C(j)) = X(i, j): sequential writes, a repeated index is overwritten by its last
-// occurrence (slice_into.cpp:51-82)
+// Y(R(i), C(j)) = X(i, j), written in row-major order of X: when an index occurs more than
+// once the last write wins (slice_into.cpp:51-82)
 template <typename DerivedX, typename DerivedY, typename DerivedR, typename DerivedC>
 inline void slice_into(const Eigen::MatrixBase<DerivedX>& X, const Eigen::MatrixBase<DerivedR>& R,
                        const Eigen::MatrixBase<DerivedC>& C, Eigen::PlainObjectBase<DerivedY>& Y) {
-  const int xm = static_cast<int>(X.rows()), xn = static_cast<int>(X.cols());
-  for (int i = 0; i < xm; i++)
-    for (int j = 0; j < xn; j++) Y(int(R(i)), int(C(j))) = X(i, j);
+  for (Eigen::Index i = 0; i < X.rows(); i++)
+    for (Eigen::Index j = 0; j < X.cols(); j++) Y(static_cast<Eigen::Index>(R(i)), static_cast<Eigen::Index>(C(j))) = X(i, j);
 }
 
-// rows (dim 1) or columns (dim 2) of Y (slice_into.cpp:84-117)
+// rows (dim == 1) or columns (dim == 2) of Y (slice_into.cpp:84-117)
 template <typename MatX, typename MatY, typename DerivedR>
 inline void slice_into(const MatX& X, const Eigen::MatrixBase<DerivedR>& R, const int dim, MatY& Y) {
-  Eigen::Matrix<int, Eigen::Dynamic, 1> C;
-  switch (dim) {
-    case 1:
-      if (X.cols() == 0) return;
-      C = Eigen::Matrix<int, Eigen::Dynamic, 1>::LinSpaced(X.cols(), 0, static_cast<int>(X.cols() - 1));
-      return slice_into(X, R, C, Y);
-    case 2:
-      if (X.rows() == 0) return;
-      C = Eigen::Matrix<int, Eigen::Dynamic, 1>::LinSpaced(X.rows(), 0, static_cast<int>(X.rows() - 1));
-      return slice_into(X, C, R, Y);
-    default:
-      return;
+  typedef Eigen::Matrix<int, Eigen::Dynamic, 1> IndexVector;
+  if (dim == 1 && X.cols() > 0) {
+    const IndexVector all = IndexVector::LinSpaced(X.cols(), 0, static_cast<int>(X.cols() - 1));
+    slice_into(X, R, all, Y);
+  } else if (dim == 2 && X.rows() > 0) {
+    const IndexVector all = IndexVector::LinSpaced(X.rows(), 0, static_cast<int>(X.rows() - 1));
+    slice_into(X, all, R, Y);
   }
 }
 }  // namespace igl
