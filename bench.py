@@ -209,6 +209,20 @@ def cpu_iterations(pr, warmup: int, steps: int, impl: str = "port"):
     return times
 
 
+def cpu_baseline(pr, nc: int):
+    """The `cpu_baseline` object of the GPU line: `nc` solve-loop iterations on one host core."""
+    impl, kind, what = cpu_impl()
+    times = cpu_iterations(pr, 1, nc, impl)
+    cpu = {"value": nc / sum(times), "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{nc} solve-loop iterations (residual norm + V(2,2)) of the same problem; {what}; "
+                     "single thread (the reference path is single-threaded)",
+           "host_cores_available": os.cpu_count()}
+    if impl != "port":  # the C restatement beside it
+        tp = cpu_iterations(pr, 1, max(nc // 2, 3), "port")
+        cpu["port_value"] = len(tp) / sum(tp)
+    return cpu
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -440,16 +454,7 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        nc = args.cpu_steps
-        impl, kind, what = cpu_impl()
-        times = cpu_iterations(pr, 1, nc, impl)
-        cpu = {"value": nc / sum(times), "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": f"{nc} solve-loop iterations (residual norm + V(2,2)) of the same problem; {what}; "
-                         "single thread (the reference path is single-threaded)",
-               "host_cores_available": os.cpu_count()}
-        if impl != "port":  # the C restatement beside it
-            tp = cpu_iterations(pr, 1, max(nc // 2, 3), "port")
-            cpu["port_value"] = len(tp) / sum(tp)
+        cpu = cpu_baseline(pr, args.cpu_steps)
     barrier()
     if rank == 0:
         line = {

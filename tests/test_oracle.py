@@ -137,3 +137,29 @@ def test_known_order_and_duplicates(problems):
     auk = ora.matrix(0, "Auk")
     A = pr.A.tocsr()
     assert abs(auk - A[unk][:, known]).max() == 0
+
+
+def test_bench_cpu_arms_run_on_a_small_problem():
+    """bench.py's CPU legs (cpu_baseline of the GPU line, the --impl reference line) on a small
+    workload: they must run without a GPU and name what they timed."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    pr = bench.build_problem(5, 3)
+    cpu = bench.cpu_baseline(pr, 3)
+    assert cpu["value"] > 0 and cpu["cores"] == 1 and cpu["kind"] in ("reference", "port")
+    if cpu["kind"] == "reference":
+        assert cpu["port_value"] > 0
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--subdiv", "5",
+                          "--levels", "3", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == cpu["kind"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
