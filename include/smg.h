@@ -233,6 +233,11 @@ int smg_get_diag(smg_handle *h, int lv, double *diag);
 /* smoother schedule: number of phases (colours or wavefront levels) on level lv
  * and, if phase_of_row != NULL, the phase of every row (reference numbering). */
 int smg_get_phases(const smg_handle *h, int lv, int *n_phases, int *phase_of_row);
+/* the library's row numbering of level lv: perm[r] = reference row stored at position r.
+ * Rows are grouped (DESIGN.md sections 3 and 6): by smoother phase; on a row-partitioned level
+ * by (part, phase); on the replicated level below one by (phase, part).  *n_groups receives the
+ * number of groups and, if group_ptr != NULL, group_ptr[0..*n_groups] their row offsets. */
+int smg_get_row_order(const smg_handle *h, int lv, int *perm, int *n_groups, int *group_ptr);
 /* storage statistics of level lv's SELL-32 matrix: stored (padded) entries */
 int smg_level_padded_nnz(const smg_handle *h, int lv, int64_t *padded);
 

@@ -111,6 +111,7 @@ SIGNATURES = {
     "smg_matrix_copy": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _dp]),
     "smg_get_diag": (C.c_int, [_vp, C.c_int, _dp]),
     "smg_get_phases": (C.c_int, [_vp, C.c_int, _ip, _ip]),
+    "smg_get_row_order": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "smg_level_padded_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_level_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_level_dep_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),

@@ -1985,6 +1985,16 @@ int smg_get_phases(const smg_handle* h, int lv, int* n_phases, int* phase_of_row
   return SMG_OK;
 }
 
+int smg_get_row_order(const smg_handle* h, int lv, int* perm, int* n_groups, int* group_ptr) {
+  SMG_TRY(check_ready(h, false));
+  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size())) return SMG_E_INVALID;
+  const smg::LevelPlan& L = h->plan.lv[lv];
+  if (perm) std::copy(L.order.perm.begin(), L.order.perm.end(), perm);
+  if (n_groups) *n_groups = static_cast<int>(L.order.phase_ptr.size()) - 1;
+  if (group_ptr) std::copy(L.order.phase_ptr.begin(), L.order.phase_ptr.end(), group_ptr);
+  return SMG_OK;
+}
+
 int smg_level_padded_nnz(const smg_handle* h, int lv, int64_t* padded) {
   SMG_TRY(check_ready(h, false));
   if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !padded) return SMG_E_INVALID;

@@ -376,6 +376,16 @@ class Solver:
         self._check(self._lib.smg_get_phases(self._h, lv, C.byref(n), _ip(out)))
         return n.value, out
 
+    def row_order(self, lv):
+        """-> (perm, group_ptr): perm[r] = reference row at position r of the library's numbering,
+        group_ptr = row offsets of the (part / phase) groups."""
+        ng = C.c_int(0)
+        self._check(self._lib.smg_get_row_order(self._h, lv, None, C.byref(ng), None))
+        perm = np.empty(self.level_rows(lv), dtype=np.int32)
+        gp = np.empty(ng.value + 1, dtype=np.int32)
+        self._check(self._lib.smg_get_row_order(self._h, lv, _ip(perm), C.byref(ng), _ip(gp)))
+        return perm, gp
+
     def padded_nnz(self, lv) -> int:
         v = C.c_int64(0)
         self._check(self._lib.smg_level_padded_nnz(self._h, lv, C.byref(v)))

@@ -122,3 +122,33 @@ def test_dist_argument_checks(problems):
     s.dist_init(0, 2)
     with pytest.raises(SmgError):
         s.dist_handle()  # plan-only: nothing to export
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_row_numbering_groups_rows_by_part_and_phase(problems, world):
+    pr = problems["sphere"]
+    s = _plan(pr, 1 % world, world, dist_levels=2) if world > 1 else Solver(device="none").set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    for lv in range(s.num_levels()):
+        n = s.level_rows(lv)
+        perm, gp = s.row_order(lv)
+        assert np.array_equal(np.sort(perm), np.arange(n))  # a permutation
+        nph, phase = s.phases(lv)
+        part = s.dist_part(lv) if world > 1 else np.zeros(n, dtype=np.int32)
+        li = s.dist_level_info(lv) if world > 1 else {"layout": 0, "parts": 1}
+        W = li["parts"]
+        assert gp[0] == 0 and gp[-1] == n and np.all(np.diff(gp) >= 0) and len(gp) - 1 == W * nph
+        # rows of a group share (part, phase); groups are ordered (part, phase) on a partitioned
+        # level, (phase, part) on the split level, (phase) otherwise
+        for g in range(len(gp) - 1):
+            rows = perm[gp[g]:gp[g + 1]]
+            if li["layout"] == 1:
+                want_part, want_phase = divmod(g, nph)
+            elif li["layout"] == 2:
+                want_phase, want_part = divmod(g, W)
+            else:
+                want_part, want_phase = 0, g
+            assert np.all(phase[rows] == want_phase) and np.all(part[rows] == want_part), (lv, g)
+        if li["layout"] == 1:  # this rank's rows are one contiguous range
+            me = s.dist_info()["rank"]
+            assert np.all(part[perm[li["own_begin"]:li["own_end"]]] == me)
+            assert li["own_end"] - li["own_begin"] == int(np.sum(part == me))
