@@ -74,6 +74,8 @@ def _declare(L):
         L.orc_matrix_copy.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp]
         L.orc_get_diag.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_coarse_bandwidth.argtypes = [C.c_void_p]
+        if hasattr(L, "orc_iterate_mt"):
+            L.orc_iterate_mt.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int]
     return L
 
 
@@ -141,6 +143,16 @@ class Oracle:
             rc = self._L.orc_set_prolongation(self._h, l, p.shape[0], p.shape[1], _i(ip), _i(ix), _d(vv))
             assert rc == 0
         self.n = None
+
+    def iterate_mt(self, bu, zu, cycles, threads=0):
+        """NOT the reference algorithm: OpenMP multicolour Gauss-Seidel + row-parallel products,
+        `cycles` x (residual norm + V(2,2)); -> (zu, r_his, threads used).  C port only."""
+        b, k = _colmajor(bu)
+        x, _ = _colmajor(zu)
+        x = x.copy()
+        r = np.zeros(cycles)
+        used = self._L.orc_iterate_mt(self._h, _d(b), _d(x), k, cycles, _d(r), int(threads))
+        return _from_colmajor(x, self.level_rows(0), k, np.ndim(zu)), r, int(used)
 
     def refresh_count(self) -> int:
         """precompute calls served by a numeric-only refresh (adapter build of the harness only)"""

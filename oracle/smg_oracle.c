@@ -34,6 +34,9 @@
  * Build:  gcc -O3 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -719,6 +722,162 @@ void orc_iterate(const orc_solver *s, const double *bu, double *zu, int k, int c
     orc_vcycle(s, bu, 2, 2, 0, zu, k);
   }
   free(tmp);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Multi-threaded CPU variant (OpenMP) -- NOT the reference algorithm.          */
+/* The reference path is single-threaded lexicographic Gauss-Seidel.  For        */
+/* context only (bench.py reports it beside the reference arm, labelled), this   */
+/* runs the same V(2,2) iteration the way a CPU would be used in parallel:       */
+/* greedy multicolour Gauss-Seidel (rows of one colour in parallel) and          */
+/* row-parallel products (A read column-as-row like the smoother does, P / PT    */
+/* through each other's CSC).  Same fixed point, different sweep order.          */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int ncol;
+  int *ptr;  /* ncol + 1 */
+  int *rows; /* n, grouped by colour */
+} orc_colouring;
+
+static orc_colouring *colour_greedy(const orc_csc *A) {
+  int n = A->rows;
+  orc_colouring *c = (orc_colouring *)calloc(1, sizeof(orc_colouring));
+  int *col = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int *stamp = (int *)malloc(sizeof(int) * 64);
+  int cap = 64, nc = 0;
+  for (int i = 0; i < cap; i++) stamp[i] = -1;
+  for (int v = 0; v < n; v++) col[v] = -1;
+  for (int v = 0; v < n; v++) {
+    for (int p = A->colptr[v]; p < A->colptr[v + 1]; p++) {
+      int w = A->rowidx[p];
+      if (w != v && col[w] >= 0) stamp[col[w]] = v;
+    }
+    int k = 0;
+    while (k < nc && stamp[k] == v) k++;
+    if (k == nc) {
+      if (nc == cap) {
+        cap *= 2;
+        stamp = (int *)realloc(stamp, sizeof(int) * (size_t)cap);
+        for (int i = nc; i < cap; i++) stamp[i] = -1;
+      }
+      nc++;
+    }
+    col[v] = k;
+  }
+  c->ncol = nc;
+  c->ptr = (int *)calloc((size_t)nc + 1, sizeof(int));
+  c->rows = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int v = 0; v < n; v++) c->ptr[col[v] + 1]++;
+  for (int k = 0; k < nc; k++) c->ptr[k + 1] += c->ptr[k];
+  int *nx = (int *)malloc(sizeof(int) * (size_t)(nc > 0 ? nc : 1));
+  for (int k = 0; k < nc; k++) nx[k] = c->ptr[k];
+  for (int v = 0; v < n; v++) c->rows[nx[col[v]]++] = v;
+  free(nx);
+  free(col);
+  free(stamp);
+  return c;
+}
+
+static void colouring_free(orc_colouring *c) {
+  if (!c) return;
+  free(c->ptr);
+  free(c->rows);
+  free(c);
+}
+
+/* y = M^T-as-rows x: y[j] = sum over the stored entries of CSC column j of val * x[row] */
+static void mt_gather_cols(const orc_csc *M, const double *x, int ldx, double *y, int ldy, int k) {
+  for (int c = 0; c < k; c++) {
+    const double *xc = x + (size_t)c * ldx;
+    double *yc = y + (size_t)c * ldy;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < M->cols; j++) {
+      double s = 0;
+      for (int p = M->colptr[j]; p < M->colptr[j + 1]; p++) s += M->val[p] * xc[M->rowidx[p]];
+      yc[j] = s;
+    }
+  }
+}
+
+static void mt_relax(const orc_csc *A, const double *d, const orc_colouring *col, int iters,
+                     const double *B, double *u, int k) {
+  int n = A->rows;
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < k; c++) {
+      const double *b = B + (size_t)c * n;
+      double *x = u + (size_t)c * n;
+      for (int q = 0; q < col->ncol; q++) {
+#pragma omp parallel for schedule(static)
+        for (int t = col->ptr[q]; t < col->ptr[q + 1]; t++) {
+          int i = col->rows[t];
+          double s = 0;
+          for (int p = A->colptr[i]; p < A->colptr[i + 1]; p++) {
+            int r = A->rowidx[p];
+            if (r != i) s += A->val[p] * x[r];
+          }
+          x[i] = (b[i] - s) / d[i];
+        }
+      }
+    }
+}
+
+static void mt_vcycle(const orc_solver *s, orc_colouring **cols, const double *B, int lv, double *u,
+                      int k) {
+  if (lv == s->nlev - 1) {
+    orc_coarse_solve(s, B, u, k);
+    return;
+  }
+  const orc_csc *A = s->mg[lv].A;
+  int n = A->rows, nc = s->mg[lv + 1].PT->rows;
+  mt_relax(A, s->mg[lv].A_diag, cols[lv], 2, B, u, k);
+  double *r = (double *)malloc(sizeof(double) * (size_t)n * k + 8);
+  mt_gather_cols(A, u, n, r, n, k);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n * k; i++) r[i] = B[i] - r[i];
+  double *rc = (double *)malloc(sizeof(double) * (size_t)nc * k + 8);
+  mt_gather_cols(s->mg[lv + 1].P, r, n, rc, nc, k); /* PT r: row c of PT = column c of P */
+  double *uc = (double *)calloc((size_t)nc * k + 1, sizeof(double));
+  mt_vcycle(s, cols, rc, lv + 1, uc, k);
+  mt_gather_cols(s->mg[lv + 1].PT, uc, nc, r, n, k); /* P uc: row f of P = column f of PT */
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n * k; i++) u[i] = u[i] + r[i];
+  mt_relax(A, s->mg[lv].A_diag, cols[lv], 2, B, u, k);
+  free(r);
+  free(rc);
+  free(uc);
+}
+
+/* `cycles` x (residual norm + multicolour V(2,2)) on the unknown-sized system with `threads`
+ * OpenMP threads (<= 0: the runtime's default).  Returns the number of threads used. */
+int orc_iterate_mt(const orc_solver *s, const double *bu, double *zu, int k, int cycles,
+                   double *r_his, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+  int used = omp_get_max_threads();
+#else
+  int used = 1;
+  (void)threads;
+#endif
+  orc_colouring **cols = (orc_colouring **)calloc((size_t)s->nlev, sizeof(orc_colouring *));
+  for (int lv = 0; lv + 1 < s->nlev; lv++) cols[lv] = colour_greedy(s->mg[lv].A);
+  const orc_csc *A = s->mg[0].A;
+  int n = A->rows;
+  double *tmp = (double *)malloc(sizeof(double) * (size_t)n * k + 8);
+  for (int it = 0; it < cycles; it++) {
+    mt_gather_cols(A, zu, n, tmp, n, k);
+    double ss = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ss)
+    for (long i = 0; i < (long)n * k; i++) {
+      double d = bu[i] - tmp[i];
+      ss += d * d;
+    }
+    r_his[it] = sqrt(ss);
+    mt_vcycle(s, cols, bu, 0, zu, k);
+  }
+  free(tmp);
+  for (int lv = 0; lv < s->nlev; lv++) colouring_free(cols[lv]);
+  free(cols);
+  return used;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -163,3 +163,17 @@ def test_bench_cpu_arms_run_on_a_small_problem():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == cpu["kind"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_parallel"]["value"] > 0 and line["cpu_parallel"]["kind"] == "variant"
+
+
+def test_parallel_cpu_variant_reaches_the_same_solution(problems):
+    """orc_iterate_mt (OpenMP multicolour Gauss-Seidel; context for the benchmark, not the
+    reference algorithm) converges to the solution of the reference-order iteration"""
+    pr = problems["sphere_pad"]
+    ora = Oracle(pr.P).precompute(pr.A, pr.known)
+    bu = np.ascontiguousarray(pr.rhs[ora.unknown])
+    z_seq, r_seq = ora.iterate(bu, np.zeros_like(bu), 14)
+    for threads in (1, 3):
+        z_mt, r_mt, used = ora.iterate_mt(bu, np.zeros_like(bu), 14, threads)
+        assert used >= 1 and r_mt[-1] < 1e-9 * r_mt[0]
+        assert np.linalg.norm(z_mt - z_seq) <= 1e-8 * np.linalg.norm(z_seq)
