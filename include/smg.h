@@ -137,6 +137,23 @@ int smg_solve_device(smg_handle *h, const double *d_RHS, const double *d_known_v
                      const double *d_z0, int k, double tol, int max_iter, double *d_z,
                      double *r_his, int *n_his, int *converged);
 
+/* ---- mean-curvature-flow step with device-side assembly -------------------------------
+ * Replaces the per-step body of 05_example_mean_curvature_flow/main.cpp:66-76:
+ *   M = massmatrix(U, F, BARYCENTRIC); LHS = M - delta * L; RHS = M * U;
+ *   min_quad_with_fixed_mg_precompute(LHS, ...); min_quad_with_fixed_mg_solve(RHS, Upre, ..., tol, ...)
+ * Only U crosses the bus per step (24 bytes per vertex each way instead of the whole LHS).
+ * Precondition: smg_precompute in the variant without fixed values (n_known < 0) with any
+ * SPD matrix that has the sparsity pattern of L (M - delta * L has it: L stores its diagonal;
+ * e.g. the first step's system, or I - L).
+ * smg_mcf_setup: F is nF x 3 column-major (Eigen::MatrixXi), L_val are the values of the
+ * cotangent matrix in the CSC order of that pattern (igl::cotmatrix(V, F, L), computed once).
+ * smg_mcf_step: U, U_out are nV x 3 column-major; the rest as smg_solve (z0 = U).
+ * STATUS: written in round 1 after the round's GPU time was spent; its arithmetic core
+ * (csrc/mcf_core.hpp) is tested on the CPU, the entry points have not run on a GPU yet. */
+int smg_mcf_setup(smg_handle *h, int nV, int nF, const int *F, const double *L_val, double delta);
+int smg_mcf_step(smg_handle *h, const double *U, double tol, int max_iter, double *U_out,
+                 double *r_his, int *n_his, int *converged);
+
 /* ---- mg_VCycle.h operators (host buffers, level sizes per smg_level_rows) ---
  * Vectors are in the caller's (reference) row numbering of that level. */
 /* mg_VCycle (src/mg_VCycle.cpp:3-59): one V(pre,post)-cycle from level lv down;

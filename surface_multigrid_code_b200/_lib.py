@@ -83,6 +83,8 @@ SIGNATURES = {
     "smg_update_values": (C.c_int, [_vp, _dp]),
     "smg_solve": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp, _dp, _ip, _ip]),
     "smg_solve_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, _vp, _dp, _ip, _ip]),
+    "smg_mcf_setup": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, C.c_double]),
+    "smg_mcf_step": (C.c_int, [_vp, _dp, C.c_double, C.c_int, _dp, _dp, _ip, _ip]),
     "smg_vcycle": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int]),
     "smg_relax": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int]),
     "smg_apply_A": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int]),

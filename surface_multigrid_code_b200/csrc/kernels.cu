@@ -13,6 +13,7 @@
 // without FMA (x86-64 baseline, 03_mg_solver/CMakeLists.txt:2,21-24) and bit
 // parity in wavefront mode depends on it.
 #include "kernels.hpp"
+#include "mcf_core.hpp"
 
 #include <algorithm>
 #include <string>
@@ -1750,6 +1751,41 @@ void preload_kernels() {
   preload_one(permute_in_kernel);
   preload_one(permute_out_kernel);
   cudaGetLastError();
+}
+
+// ---- mean-curvature-flow assembly on the device (mcf_core.hpp holds the arithmetic) ------
+namespace {
+__global__ void mcf_face_kernel(int nV, int nF, const int* __restrict__ F, const double* __restrict__ U,
+                                double* __restrict__ dblA) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < nF) dblA[f] = mcf_face_doublearea(U, nV, F[f], F[f + nF], F[f + 2 * nF]);
+}
+__global__ void mcf_vertex_kernel(int nV, const int* __restrict__ vf_ptr, const int* __restrict__ vf_face,
+                                  const double* __restrict__ dblA, double* __restrict__ mass) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nV) mass[v] = mcf_vertex_mass(dblA, vf_face, vf_ptr[v], vf_ptr[v + 1]);
+}
+__global__ void mcf_lhs_kernel(int nnz, const int* __restrict__ rowidx, const int* __restrict__ colidx,
+                               const double* __restrict__ mass, double delta, const double* __restrict__ Lval,
+                               double* __restrict__ a_val) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) a_val[p] = mcf_lhs_entry(rowidx[p] == colidx[p] ? mass[colidx[p]] : 0.0, delta, Lval[p]);
+}
+__global__ void mcf_rhs_kernel(int nV, int k, const double* __restrict__ mass, const double* __restrict__ U,
+                               double* __restrict__ rhs) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nV)
+    for (int c = 0; c < k; c++) rhs[v + (size_t)c * nV] = __dmul_rn(mass[v], U[v + (size_t)c * nV]);
+}
+}  // namespace
+
+void launch_mcf_assemble(int nV, int nF, const int* F, const double* U, const int* vf_ptr, const int* vf_face,
+                         double* dblA, double* mass, int nnz, const int* rowidx, const int* colidx, double delta,
+                         const double* Lval, double* a_val, int k, double* rhs, cudaStream_t st) {
+  if (nF > 0) mcf_face_kernel<<<blocks_for(nF, 256), 256, 0, st>>>(nV, nF, F, U, dblA);
+  if (nV > 0) mcf_vertex_kernel<<<blocks_for(nV, 256), 256, 0, st>>>(nV, vf_ptr, vf_face, dblA, mass);
+  if (nnz > 0) mcf_lhs_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, rowidx, colidx, mass, delta, Lval, a_val);
+  if (nV > 0) mcf_rhs_kernel<<<blocks_for(nV, 256), 256, 0, st>>>(nV, k, mass, U, rhs);
 }
 
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {

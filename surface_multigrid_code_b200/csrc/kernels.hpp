@@ -195,6 +195,13 @@ void launch_dense_sym_add(const double* tiles, const double* b, double* u, doubl
 void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
                            cudaStream_t st);
 
+// ---- mean-curvature-flow step: device-side assembly (05_example_mean_curvature_flow/main.cpp:66-69)
+// dblA (nF), mass (nV) are scratch; a_val receives M - delta * L in the CSC order of
+// (rowidx, colidx); rhs = M * U (nV x k column-major).  Four launches.
+void launch_mcf_assemble(int nV, int nF, const int* F, const double* U, const int* vf_ptr, const int* vf_face,
+                         double* dblA, double* mass, int nnz, const int* rowidx, const int* colidx, double delta,
+                         const double* Lval, double* a_val, int k, double* rhs, cudaStream_t st);
+
 // ---- solve-time gather / scatter ----------------------------------------------
 // zu[r] = z0[g[r]] ; bu[r] = RHS[g[r]] - sum_q Auk(row r, q) kv[q]   (per column)
 void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,

@@ -278,6 +278,14 @@ struct smg_handle {
   std::map<std::tuple<int, int, int, int, int>, TailLists> tails;  // (first level, pre, post, k0, kk)
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // mean-curvature-flow assembly (smg_mcf_*)
+  struct {
+    bool ready = false;
+    int nV = 0, nF = 0;
+    double delta = 0.0;
+    DevBuf<int> F, vf_ptr, vf_face;
+    DevBuf<double> Lval, dblA, mass, U, rhs, z;
+  } mcf;
   bool no_prefetch = false;
   bool async_alloc = false;
   DistCtx dist;
@@ -1373,6 +1381,8 @@ void smg_destroy(smg_handle* h) {
     h->ainv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
     h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
+    h->mcf.F.release(); h->mcf.vf_ptr.release(); h->mcf.vf_face.release(); h->mcf.Lval.release();
+    h->mcf.dblA.release(); h->mcf.mass.release(); h->mcf.U.release(); h->mcf.rhs.release(); h->mcf.z.release();
     DistCtx& D = h->dist;
     D.ctrl.release(); D.normv.release(); D.x_norm = ExchDev();
     for (size_t q = 0; q < D.peer.size(); q++)
@@ -1527,6 +1537,79 @@ int smg_solve(smg_handle* h, const double* RHS, const double* known_val, const d
   h->timings[0] = t1 - t0;
   h->timings[1] = t2 - t1;
   h->timings[2] = t3 - t2;
+  return SMG_OK;
+}
+
+// ---- mean-curvature-flow step ------------------------------------------------------
+int smg_mcf_setup(smg_handle* h, int nV, int nF, const int* F, const double* L_val, double delta) {
+  SMG_TRY(check_ready(h, true));
+  if (!F || !L_val || nV < 1 || nF < 0) return fail(h, SMG_E_INVALID, "bad argument");
+  const smg::Plan& pl = h->plan;
+  if (pl.has_fixed) return fail(h, SMG_E_STATE, "smg_mcf_* needs the precompute variant without fixed values");
+  if (nV != pl.n) return fail(h, SMG_E_INVALID, "nV does not match the precomputed matrix");
+  for (int i = 0; i < 3 * nF; i++)
+    if (F[i] < 0 || F[i] >= nV) return fail(h, SMG_E_INVALID, "face index out of range");
+  SMG_TRY(set_device(h));
+  auto& m = h->mcf;
+  m.ready = false;
+  m.nV = nV;
+  m.nF = nF;
+  m.delta = delta;
+  // incident faces of every vertex in the order setFromTriplets sums them: corner 0 (faces
+  // ascending), corner 1, corner 2 (massmatrix_intrinsic.cpp:59-64)
+  std::vector<int> ptr(static_cast<size_t>(nV) + 1, 0), faces(static_cast<size_t>(3) * nF);
+  for (int i = 0; i < 3 * nF; i++) ptr[static_cast<size_t>(F[i]) + 1]++;
+  for (int v = 0; v < nV; v++) ptr[static_cast<size_t>(v) + 1] += ptr[static_cast<size_t>(v)];
+  {
+    std::vector<int> nx(ptr.begin(), ptr.end() - 1);
+    for (int c = 0; c < 3; c++)
+      for (int f = 0; f < nF; f++) faces[static_cast<size_t>(nx[static_cast<size_t>(F[f + c * nF])]++)] = f;
+  }
+  SMG_CUDA(h, m.F.upload(std::vector<int>(F, F + static_cast<size_t>(3) * nF), h->stream));
+  SMG_CUDA(h, m.vf_ptr.upload(ptr, h->stream));
+  SMG_CUDA(h, m.vf_face.upload(faces, h->stream));
+  SMG_CUDA(h, m.Lval.upload(std::vector<double>(L_val, L_val + pl.LHS.nnz()), h->stream));
+  SMG_CUDA(h, m.dblA.alloc(static_cast<size_t>(std::max(nF, 1))));
+  SMG_CUDA(h, m.mass.alloc(static_cast<size_t>(nV)));
+  SMG_CUDA(h, m.U.alloc(static_cast<size_t>(nV) * 3));
+  SMG_CUDA(h, m.rhs.alloc(static_cast<size_t>(nV) * 3));
+  SMG_CUDA(h, m.z.alloc(static_cast<size_t>(nV) * 3));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  m.ready = true;
+  return SMG_OK;
+}
+
+int smg_mcf_step(smg_handle* h, const double* U, double tol, int max_iter, double* U_out, double* r_his,
+                 int* n_his, int* converged) {
+  SMG_TRY(check_ready(h, true));
+  auto& m = h->mcf;
+  if (!m.ready) return fail(h, SMG_E_STATE, "smg_mcf_setup has not been called");
+  if (!U || !U_out || !r_his || !n_his || !converged || max_iter < 0) return fail(h, SMG_E_INVALID, "bad argument");
+  SMG_TRY(set_device(h));
+  const double t0 = now_ms();
+  const size_t cnt = static_cast<size_t>(m.nV) * 3;
+  SMG_CUDA(h, cudaMemcpyAsync(m.U.p, U, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  LevelDev& L0 = h->lv[0];
+  // LHS = M(U) - delta * L straight into the device copy of the caller's matrix values
+  // (free variant: LHS has the caller's pattern and order), RHS = M * U
+  smg::launch_mcf_assemble(m.nV, m.nF, m.F.p, m.U.p, m.vf_ptr.p, m.vf_face.p, m.dblA.p, m.mass.p,
+                           h->plan.LHS.nnz(), L0.a_rowidx.p, L0.a_col.p, m.delta, m.Lval.p, h->a_in.p, 3,
+                           m.rhs.p, h->stream);
+  h->launches += 4;
+  SMG_TRY(check_launch(h, "mcf assemble"));
+  SMG_TRY(numeric_setup(h));  // Galerkin products, diagonals, coarse factorisation: as smg_update_values
+  const double t1 = now_ms();
+  const int rc = solve_core(h, m.rhs.p, nullptr, m.U.p, 3, tol, max_iter, m.z.p, r_his, n_his, converged);
+  if (rc != SMG_OK) return rc;
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double t2 = now_ms();
+  SMG_TRY(drain_if_shared(h));
+  SMG_CUDA(h, cudaMemcpyAsync(U_out, m.z.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->timings[0] = 0.0;
+  h->timings[4] = t1 - t0;  // assembly + numeric precompute
+  h->timings[1] = t2 - t1;
+  h->timings[2] = now_ms() - t2;
   return SMG_OK;
 }
 

@@ -274,6 +274,34 @@ class Solver:
         self._check(rc)
         return r_his[: nh.value].copy(), bool(conv.value)
 
+    # -- mean-curvature-flow step with device-side assembly -------------------------------------
+    def mcf_setup(self, F, L, delta: float = 0.01):
+        """F: (nF, 3) int faces; L: scipy sparse cotangent matrix with the pattern the handle was
+        precomputed with (05_example_mean_curvature_flow/main.cpp:41, computed once)."""
+        F = np.asarray(F)
+        Fb = np.ascontiguousarray(F.T, dtype=np.int32).reshape(-1)  # column-major nF x 3
+        L = L.tocsc()
+        if not L.has_sorted_indices:
+            L = L.copy()
+            L.sort_indices()
+        vv = _f64(L.data)
+        if vv.size != self.nnz:
+            raise ValueError("L does not have the precomputed pattern")
+        self._check(self._lib.smg_mcf_setup(self._h, self.n, F.shape[0], _ip(Fb), _dp(vv), float(delta)))
+        return self
+
+    def mcf_step(self, U, tol: float = 5e-7, max_iter: int = 20):
+        """One flow step (main.cpp:66-76) -> (U_new, r_his, converged); U is (n, 3)."""
+        u, k, nd = _colmajor(U)
+        if k != 3 or u.size != self.n * 3:
+            raise ValueError("U must be n x 3")
+        out = np.empty(self.n * 3)
+        r_his = np.zeros(max(int(max_iter), 1))
+        nh, conv = C.c_int(0), C.c_int(0)
+        self._check(self._lib.smg_mcf_step(self._h, _dp(u), float(tol), int(max_iter), _dp(out), _dp(r_his),
+                                           C.byref(nh), C.byref(conv)))
+        return _from_colmajor(out, self.n, 3, 2), r_his[: nh.value].copy(), bool(conv.value)
+
     # -- mg_VCycle.h operators -------------------------------------------------------------
     def level_rows(self, lv: int) -> int:
         return int(self._lib.smg_level_rows(self._h, lv))

@@ -157,3 +157,11 @@ def test_file_rendezvous_all_gathers_blobs(tmp_path):
     out = C.create_string_buffer(2 * nbytes)
     assert lib.smg_rendezvous_files(str(tmp_path).encode(), b"t1", 0, 2, mine[0], nbytes, out, 200) == 10
     assert lib.smg_rendezvous_files(b"/nonexistent-dir", b"t", 0, 2, mine[0], nbytes, out, 200) == 1
+
+
+def test_mcf_entry_points_need_a_device(problems):
+    pr = problems["mcf"]
+    s = Solver(device="none").set_hierarchy(pr.P).precompute(pr.A, None)
+    with pytest.raises(SmgError) as e:
+        s.mcf_setup(pr.F, pr.A)
+    assert e.value.status == 5  # SMG_E_STATE: plan-only handles cannot compute
