@@ -252,7 +252,8 @@ bool solve_impl(const min_quad_with_fixed_mg_data& data,
         smg_solve(h, RHS.derived().data(), known_val, z0.derived().data(), k, tolerance, maxIter,
                   z.derived().data(), his.data(), &n_his, &converged),
         "smg_solve");
-  r_his.insert(r_his.end(), his.begin(), his.begin() + n_his);  // the reference push_back's (cpp:335)
+  // the reference clears r_his at the start of every solve (cpp:105, :327), then push_back's (cpp:335)
+  r_his.assign(his.begin(), his.begin() + n_his);
   return converged != 0;
 }
 
@@ -260,6 +261,30 @@ bool solve_impl(const min_quad_with_fixed_mg_data& data,
 
 // precompute calls that were served by a numeric-only refresh (tests)
 extern "C" int smg_adapter_refresh_count(void) { return g_refreshes; }
+
+// The registry is keyed by the ADDRESS of the caller's `data` / `mg` objects (the reference's
+// structs have no destructor hook): a handle lives until the same objects are precomputed again
+// or until the process ends.  A caller that destroys its objects earlier (the stack-allocated
+// solverData of 05_example_mean_curvature_flow/main.cpp:72) can release the device memory with
+// this call; it is optional: a later precompute at a recycled address never reuses stale state
+// (the fingerprint check compares pattern, fixed set and hierarchy), it only replaces the entry.
+// Returns the number of registry entries removed.
+extern "C" int smg_adapter_release(const void* data_or_mg) {
+  auto it = registry().find(data_or_mg);
+  if (it == registry().end()) return 0;
+  std::shared_ptr<smg_handle> h = it->second;
+  int removed = 0;
+  for (auto jt = registry().begin(); jt != registry().end();)
+    if (jt->second == h) {
+      jt = registry().erase(jt);
+      removed++;
+    } else {
+      ++jt;
+    }
+  fingerprints().erase(h.get());
+  return removed;  // the handle is destroyed when `h` goes out of scope
+}
+extern "C" int smg_adapter_live_handles(void) { return static_cast<int>(fingerprints().size()); }
 
 // ---- min_quad_with_fixed_mg.h -----------------------------------------------------
 void min_quad_with_fixed_mg_precompute(const Eigen::SparseMatrix<double>& A,

@@ -58,6 +58,11 @@ typedef enum smg_smoother {
   SMG_SMOOTHER_MULTICOLOUR = 1
 } smg_smoother;
 
+/* limits: right-hand-side columns per call (k), rows of the coarsest level (its inverse is
+ * kept dense: 8 n^2 bytes during precompute) */
+#define SMG_MAX_RHS 32
+#define SMG_MAX_COARSE_ROWS 16384
+
 #define SMG_DEVICE_CURRENT (-1)
 #define SMG_DEVICE_NONE (-2) /* plan-only handle: host index planning, no CUDA */
 
@@ -148,8 +153,7 @@ int smg_solve_device(smg_handle *h, const double *d_RHS, const double *d_known_v
  * smg_mcf_setup: F is nF x 3 column-major (Eigen::MatrixXi), L_val are the values of the
  * cotangent matrix in the CSC order of that pattern (igl::cotmatrix(V, F, L), computed once).
  * smg_mcf_step: U, U_out are nV x 3 column-major; the rest as smg_solve (z0 = U).
- * STATUS: written in round 1 after the round's GPU time was spent; its arithmetic core
- * (csrc/mcf_core.hpp) is tested on the CPU, the entry points have not run on a GPU yet. */
+ * Tests: tests/test_gpu_zz_mcf.py (GPU, against the host path), tests/test_mcf_core.py (CPU). */
 int smg_mcf_setup(smg_handle *h, int nV, int nF, const int *F, const double *L_val, double delta);
 int smg_mcf_step(smg_handle *h, const double *U, double tol, int max_iter, double *U_out,
                  double *r_his, int *n_his, int *converged);

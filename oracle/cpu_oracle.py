@@ -74,6 +74,8 @@ def _declare(L):
         L.orc_matrix_copy.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _dp]
         L.orc_get_diag.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_coarse_bandwidth.argtypes = [C.c_void_p]
+        if hasattr(L, "orc_solve_twice_same_rhis"):
+            L.orc_solve_twice_same_rhis.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, _ip, _ip]
         if hasattr(L, "orc_iterate_mt"):
             L.orc_iterate_mt.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int]
     return L
@@ -274,6 +276,22 @@ class Oracle:
         conv = self._L.orc_solve(self._h, _d(b), _d(kv) if kv is not None else None, _d(x0), k,
                                  float(tol), int(max_iter), _d(z), _d(r_his), C.byref(nh))
         return _from_colmajor(z, self.n, k, np.ndim(RHS)), r_his[: nh.value].copy(), bool(conv)
+
+    def solve_twice_same_rhis(self, RHS, z0, known_val=None, tol=1e-3, max_iter=20):
+        """Two solves that reuse ONE r_his vector (k = 1): its size after each (reference: cleared per solve)."""
+        b, _ = _colmajor(RHS)
+        x0, _ = _colmajor(z0)
+        kv = None
+        if self.nknown > 0:
+            kv, _ = _colmajor(known_val if known_val is not None else np.zeros(self.nknown))
+        n1, n2 = C.c_int(0), C.c_int(0)
+        rc = self._L.orc_solve_twice_same_rhis(self._h, _d(b), _d(kv) if kv is not None else None, _d(x0),
+                                               float(tol), int(max_iter), C.byref(n1), C.byref(n2))
+        assert rc == 0
+        return n1.value, n2.value
+
+    def live_handles(self) -> int:
+        return int(self._L.orc_live_handles()) if hasattr(self._L, "orc_live_handles") else 0
 
     def iterate(self, bu, zu, cycles):
         """`cycles` x (residual norm + V(2,2)) on the unknown-sized system (timed CPU baseline)."""

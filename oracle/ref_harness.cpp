@@ -105,7 +105,20 @@ void* orc_create(int nlev) {
   return s;
 }
 
-void orc_destroy(void* h) { delete static_cast<Ref*>(h); }
+void orc_destroy(void* h) {
+  Ref* s = static_cast<Ref*>(h);
+#ifdef SMG_HARNESS_USE_ADAPTER
+  if (s) smg_adapter_release(&s->data);  // what a caller does before its solver objects die
+#endif
+  delete s;
+}
+int orc_live_handles(void) {
+#ifdef SMG_HARNESS_USE_ADAPTER
+  return smg_adapter_live_handles();
+#else
+  return 0;
+#endif
+}
 
 // what mg_precompute leaves for level lv >= 1 (src/mg_precompute.cpp:71-77)
 int orc_set_prolongation(void* h, int lv, int rows, int cols, const int* colptr, const int* rowidx,
@@ -249,6 +262,30 @@ int orc_solve(void* h, const double* RHS, const double* known_val, const double*
   for (size_t i = 0; i < hist.size(); i++) r_his[i] = hist[i];
   *n_his = static_cast<int>(hist.size());
   return ok ? 1 : 0;
+  ORC_CATCH(return -4)
+}
+
+// Two solves in a row that REUSE one r_his vector, as a caller's time-step loop would: the
+// reference clears it at the start of every solve (src/min_quad_with_fixed_mg.cpp:105, :327).
+// Returns r_his.size() after the first and after the second solve (k = 1).
+int orc_solve_twice_same_rhis(void* h, const double* RHS, const double* known_val, const double* z0, double tol,
+                              int max_iter, int* n_first, int* n_second) {
+  ORC_TRY
+  Ref* s = static_cast<Ref*>(h);
+  const Eigen::Index n = s->data.n;
+  std::vector<double> hist;
+  Quiet q;
+  Eigen::VectorXd b = vec_from(RHS, n), x0 = vec_from(z0, n), x;
+  for (int rep = 0; rep < 2; rep++) {
+    if (s->has_fixed) {
+      Eigen::VectorXd kv = vec_from(known_val, s->nknown);
+      min_quad_with_fixed_mg_solve(s->data, b, kv, x0, s->solver, tol, max_iter, s->mg, x, hist);
+    } else {
+      min_quad_with_fixed_mg_solve(s->data, b, x0, s->solver, tol, max_iter, s->mg, x, hist);
+    }
+    *(rep == 0 ? n_first : n_second) = static_cast<int>(hist.size());
+  }
+  return 0;
   ORC_CATCH(return -4)
 }
 

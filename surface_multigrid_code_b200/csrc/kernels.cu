@@ -701,12 +701,15 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
 }
 
 // ---- multi-GPU halo exchange (see kernels.hpp::XchgPeer) --------------------------------
-// Low-latency protocol without fences: every value travels as one 16-byte store
-// {value bits, epoch} into the peer's staging slot (a 16-byte aligned vector store is
-// delivered as one unit over NVLink), and the receiver polls each 16-byte word of its own
-// slot until the epoch matches.  A fence + flag protocol costs ~10 us per exchange on
-// B200 (system-scope fences wait for the NVLink round trip); this one costs one store
-// latency.  After the payload every pair of ranks exchanges one extra sync word, so a
+// Low-latency protocol without fences (the scheme of NCCL's LL protocol): a value travels as
+// two 8-byte words {low half | epoch << 32} and {high half | epoch << 32} into the peer's
+// staging slot, and the receiver polls the two words of its own slot until BOTH carry the
+// expected epoch.  Correctness needs only what PTX guarantees on every interconnect (NVLink,
+// NVSwitch, PCIe peer-to-peer, one GPU's L2): an aligned 8-byte access is single-copy atomic.
+// The two words are issued as one 16-byte vector store / load for throughput, but nothing
+// depends on the 16 bytes arriving together.  A fence + flag protocol costs ~10 us per
+// exchange on B200 (system-scope fences wait for the NVLink round trip); this one costs one
+// store latency.  After the payload every pair of ranks exchanges one extra sync word, so a
 // rank can never run two exchanges ahead of a peer even when a pair has no payload, which
 // is what makes the parity double-buffering of the slots safe.
 // Grid (ctas per peer, npeers); ctrl layout: [2] error flag, [8 + 64 + peer] exit counter,
@@ -722,15 +725,16 @@ unsigned long long g_xchg_timeout_ns = 20ull * 1000 * 1000 * 1000;
 constexpr int kXchgMaxPeers = 64;
 
 __device__ __forceinline__ void st_ll(double* slot, size_t i, double v, unsigned long long epoch) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2 * i),
-               "l"(__double_as_longlong(v)), "l"(epoch)
-               : "memory");
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+  const unsigned long long w0 = (bits & 0xffffffffull) | (epoch << 32);
+  const unsigned long long w1 = (bits >> 32) | (epoch << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2 * i), "l"(w0), "l"(w1) : "memory");
 }
 __device__ __forceinline__ bool ld_ll(const double* slot, size_t i, unsigned long long epoch, double* v) {
-  unsigned long long d, f;
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(d), "=l"(f) : "l"(slot + 2 * i) : "memory");
-  *v = __longlong_as_double(d);
-  return f == epoch;
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot + 2 * i) : "memory");
+  *v = __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+  return (w0 >> 32) == epoch && (w1 >> 32) == epoch;
 }
 
 __global__ void __launch_bounds__(kXchgThreads)

@@ -21,9 +21,12 @@
 // entry point fails with SMG_E_CUDA / SMG_E_STATE.
 #include <cuda_runtime.h>
 #include <cusolverDn.h>
+#include <signal.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -254,6 +257,7 @@ struct smg_handle {
 
   // system gather / scatter
   DevBuf<double> a_in;  // caller's A values
+  size_t a_nnz = 0;     // entries of the last precomputed A (a_in.n is a capacity, never shrinks)
   DevBuf<int> lhs_src, auk_src;
   DevBuf<int> g;                          // permuted unknown row -> caller index
   DevBuf<int> auk_ptr, auk_q, auk_pos;    // Auk by permuted row; auk_pos -> entry of Auk CSC
@@ -546,6 +550,10 @@ int upload_dist(smg_handle* h) {
 }
 
 int ensure_k(smg_handle* h, int k) {
+  // the pinned residual scratch (h_norm: 1024 doubles, flags from [32], per-rank sums from
+  // [64]) is sized for SMG_MAX_RHS columns and 64 ranks
+  if (k > SMG_MAX_RHS)
+    return fail(h, SMG_E_INVALID, "more than SMG_MAX_RHS right-hand-side columns");
   if (k <= h->kcap) return SMG_OK;
   drop_graphs(h);
   SMG_CUDA(h, h->coarse_scratch.reserve(smg::dense_sym_scratch_doubles(h->lv.back().n, k)));
@@ -918,6 +926,10 @@ int numeric_setup(smg_handle* h) {
   SMG_TRY(check_launch(h, "numeric setup"));
   // coarse factorisation (cpp:46-48, :253-254): dense Cholesky, explicit inverse
   const int nc = Lc.n;
+  if (nc > SMG_MAX_COARSE_ROWS)
+    return fail(h, SMG_E_UNSUPPORTED,
+                "coarsest level has " + std::to_string(nc) + " rows: the dense inverse supports at most " +
+                    std::to_string(SMG_MAX_COARSE_ROWS) + " (add a coarser level)");
   if (nc > 0) {
     SMG_CUDA(h, h->ainv.reserve(static_cast<size_t>(nc) * nc));
     SMG_CUDA(h, cudaMemsetAsync(h->ainv.p, 0, sizeof(double) * nc * nc, st));
@@ -1415,6 +1427,7 @@ int smg_set_hierarchy(smg_handle* h, int n_levels, const int* n_rows, const int*
   h->P_full = std::move(P);
   h->have_hierarchy = true;
   h->have_plan = false;
+  h->mcf.ready = false;
   return SMG_OK;
 }
 
@@ -1428,6 +1441,7 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
     return fail(h, SMG_E_INVALID, "A is not a valid sorted CSC matrix");
   SMG_TRY(set_device(h));
   h->have_plan = false;
+  h->mcf.ready = false;  // sized for the previous matrix
   const double t0 = now_ms();
   Csc A = make_csc(n, n, A_colptr, A_rowidx, nullptr);
   smg::PlanOptions po;
@@ -1450,6 +1464,7 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   }
   SMG_TRY(upload_plan(h));
   const int nnz = A_colptr[n];
+  h->a_nnz = static_cast<size_t>(nnz);
   SMG_CUDA(h, h->a_in.reserve(static_cast<size_t>(nnz)));
   SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
                               h->stream));
@@ -1479,7 +1494,7 @@ int smg_update_values(smg_handle* h, const double* A_val) {
   if (!A_val) return fail(h, SMG_E_INVALID, "null argument");
   SMG_TRY(set_device(h));
   const double t0 = now_ms();
-  const size_t nnz = h->a_in.n;
+  const size_t nnz = h->a_nnz;  // of the last smg_precompute, not the buffer capacity
   SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
                               h->stream));
   SMG_TRY(numeric_setup(h));
@@ -1831,39 +1846,101 @@ int smg_dist_connect(smg_handle* h, const void* all_blobs) {
   return SMG_OK;
 }
 
+// File rendezvous.  A file is {RvHeader, payload}; a reader accepts it only when the header's
+// process is alive, so the leftovers of an earlier run with the same directory and tag (dead
+// pids) are never taken for a peer's blob.  After a rank has read every blob it publishes an
+// acknowledgement that names the (pid, seq) of the blob it answers to; once every peer has
+// acknowledged, a rank removes its own blob (the small acknowledgement file stays; a later
+// round replaces it, and (pid, seq) tells a reader which round it belongs to).
+namespace {
+struct RvHeader {
+  unsigned long long magic;
+  long long pid;
+  long long seq;  // rendezvous calls made by this process so far
+};
+constexpr unsigned long long kRvMagic = 0x534d47525a563032ull;  // "SMGRZV02"
+bool pid_alive(long long pid) {
+  if (pid <= 0) return false;
+  return ::kill(static_cast<pid_t>(pid), 0) == 0 || errno == EPERM;
+}
+bool rv_publish(const std::string& path, const RvHeader& hd, const void* payload, size_t bytes) {
+  const std::string tmp = path + ".tmp." + std::to_string(hd.pid);
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return false;
+  size_t w = std::fwrite(&hd, 1, sizeof(hd), f);
+  if (bytes > 0) w += std::fwrite(payload, 1, bytes, f);
+  if (std::fclose(f) != 0 || w != sizeof(hd) + bytes) return false;
+  return std::rename(tmp.c_str(), path.c_str()) == 0;  // atomic within a file system
+}
+bool rv_read(const std::string& path, RvHeader* hd, void* payload, size_t bytes) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::vector<char> buf(sizeof(RvHeader) + bytes + 1);
+  const size_t r = std::fread(buf.data(), 1, buf.size(), f);
+  std::fclose(f);
+  if (r != sizeof(RvHeader) + bytes) return false;
+  std::memcpy(hd, buf.data(), sizeof(RvHeader));
+  if (hd->magic != kRvMagic || !pid_alive(hd->pid)) return false;  // stale: its writer is gone
+  if (bytes > 0) std::memcpy(payload, buf.data() + sizeof(RvHeader), bytes);
+  return true;
+}
+std::atomic<long long> g_rv_seq{0};
+}  // namespace
+
 int smg_rendezvous_files(const char* dir, const char* tag, int rank, int world, const void* mine,
                          size_t bytes, void* all, int timeout_ms) {
   if (!dir || !tag || !mine || !all || world < 1 || rank < 0 || rank >= world || bytes == 0)
     return SMG_E_INVALID;
   const std::string base = std::string(dir) + "/" + tag + ".";
-  {  // publish: write to a private name, then rename (atomic within a file system)
-    const std::string tmp = base + std::to_string(rank) + ".tmp." + std::to_string(static_cast<long long>(getpid()));
-    FILE* f = std::fopen(tmp.c_str(), "wb");
-    if (!f) return SMG_E_INVALID;
-    const size_t w = std::fwrite(mine, 1, bytes, f);
-    if (std::fclose(f) != 0 || w != bytes) return SMG_E_INVALID;
-    if (std::rename(tmp.c_str(), (base + std::to_string(rank)).c_str()) != 0) return SMG_E_INVALID;
-  }
+  RvHeader me;
+  me.magic = kRvMagic;
+  me.pid = static_cast<long long>(getpid());
+  me.seq = ++g_rv_seq;
+  const std::string my_blob = base + std::to_string(rank), my_ack = my_blob + ".ack";
+  if (!rv_publish(my_blob, me, mine, bytes)) return SMG_E_INVALID;
   const double t0 = now_ms();
+  std::vector<RvHeader> hd(static_cast<size_t>(world));
   std::vector<char> have(static_cast<size_t>(world), 0);
-  int missing = world;
-  while (missing > 0) {
-    for (int q = 0; q < world; q++) {
-      if (have[q]) continue;
-      FILE* f = std::fopen((base + std::to_string(q)).c_str(), "rb");
-      if (!f) continue;
-      const size_t r = std::fread(static_cast<char*>(all) + static_cast<size_t>(q) * bytes, 1, bytes, f);
-      std::fclose(f);
-      if (r == bytes) {
-        have[q] = 1;
-        missing--;
+  auto wait_all = [&](auto&& try_one) {
+    int missing = world;
+    std::fill(have.begin(), have.end(), 0);
+    while (missing > 0) {
+      for (int q = 0; q < world; q++)
+        if (!have[q] && try_one(q)) {
+          have[q] = 1;
+          missing--;
+        }
+      if (missing > 0) {
+        if (timeout_ms >= 0 && now_ms() - t0 > timeout_ms) return false;
+        usleep(2000);
       }
     }
-    if (missing > 0) {
-      if (timeout_ms >= 0 && now_ms() - t0 > timeout_ms) return SMG_E_INTERNAL;
-      usleep(2000);
-    }
+    return true;
+  };
+  // round 1: every rank's blob, written by a live process
+  if (!wait_all([&](int q) {
+        return rv_read(base + std::to_string(q), &hd[q], static_cast<char*>(all) + static_cast<size_t>(q) * bytes,
+                       bytes);
+      }))
+    return SMG_E_INTERNAL;
+  // round 2: acknowledgements.  An ack carries, per rank, the (pid, seq) of the blob its writer
+  // read; a rank is done when every peer has read THIS round's blob of it.
+  std::vector<long long> seen(static_cast<size_t>(world) * 2);
+  for (int q = 0; q < world; q++) {
+    seen[2 * q] = hd[q].pid;
+    seen[2 * q + 1] = hd[q].seq;
   }
+  if (!rv_publish(my_ack, me, seen.data(), seen.size() * sizeof(long long))) return SMG_E_INVALID;
+  std::vector<long long> theirs(seen.size());
+  if (!wait_all([&](int q) {
+        RvHeader ah;
+        if (!rv_read(base + std::to_string(q) + ".ack", &ah, theirs.data(), theirs.size() * sizeof(long long)))
+          return false;
+        return ah.pid == hd[q].pid && ah.seq == hd[q].seq && theirs[2 * rank] == me.pid &&
+               theirs[2 * rank + 1] == me.seq;
+      }))
+    return SMG_E_INTERNAL;
+  std::remove(my_blob.c_str());  // every peer has it; the ack stays until this rank's next round
   return SMG_OK;
 }
 

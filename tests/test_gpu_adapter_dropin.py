@@ -128,3 +128,19 @@ def test_repeated_precompute_with_new_values_is_a_numeric_refresh(problems, smoo
     ref.precompute(pr.A, pr.known)
     for lv in range(pr.nlev):
         assert _same_matrix(ada.matrix(lv, "A"), ref.matrix(lv, "A")), lv
+
+
+def test_r_his_is_cleared_per_solve_and_handles_are_released(problems, smoother_env):
+    """min_quad_with_fixed_mg.cpp:105/:327 clear r_his at the start of every solve: a caller that
+    reuses one vector across time steps sees the history of the LAST solve only.  Also: destroying
+    the caller's solver objects (smg_adapter_release) frees the device handle."""
+    pr = problems["sphere_pad"]
+    smoother_env(0)
+    ref = Oracle(pr.P, impl="ref").precompute(pr.A, pr.known)
+    ada = Oracle(pr.P, impl="adapter").precompute(pr.A, pr.known)
+    assert ada.solve_twice_same_rhis(pr.rhs, pr.z0, pr.known_val, 1e-8, 30) == \
+        ref.solve_twice_same_rhis(pr.rhs, pr.z0, pr.known_val, 1e-8, 30)
+    live = ada.live_handles()
+    assert live >= 1
+    ada.__del__()
+    assert Oracle(pr.P, impl="adapter").live_handles() == live - 1

@@ -174,10 +174,16 @@ def test_solve_multicolour_converges_to_same_solution(problems, name):
     assert abs(len(r_his) - len(r_ref)) <= 2
     assert r_his[0] == pytest.approx(r_ref[0], rel=1e-10)
     assert np.linalg.norm(z - z_ref) <= 1e-7 * np.linalg.norm(z_ref)
-    # the returned z really satisfies the system: recomputed by the oracle
-    nu = ora.level_rows(0)
+    # the returned z really satisfies the system: ||RHS_u - LHS z_u|| recomputed by the CPU checker
+    # (RHS_u = RHS(unknown) - Auk * known_val, min_quad_with_fixed_mg.cpp:316-318)
     zu = np.asarray(z)[ora.unknown]
-    assert zu.shape[0] == nu
+    bu = np.asarray(pr.rhs)[ora.unknown]
+    if pr.known is not None and len(pr.known) > 0:
+        bu = bu - ora.matrix(0, "Auk") @ np.asarray(pr.known_val)
+    true_res = np.linalg.norm(bu - ora.apply_A(0, zu))
+    assert true_res < tol, true_res
+    # and it is what the library measured last (or better: one more cycle ran after it)
+    assert true_res <= r_his[-1] * (1 + 1e-6) or true_res < tol
     s.close()
 
 
@@ -199,6 +205,42 @@ def test_update_values_matches_fresh_precompute(problems):
     z, r_his, _ = s.solve(pr.rhs, pr.z0, None, pr.tol, pr.max_iter)
     assert len(r_his) == len(r_ref)
     assert np.linalg.norm(z - z_ref) <= 1e-9 * np.linalg.norm(z_ref)
+    s.close()
+
+
+def test_update_values_after_a_smaller_precompute_uses_the_new_size(problems):
+    """A handle precomputed with a larger matrix and then with a smaller one must size the
+    refresh by the LAST matrix (the value buffer never shrinks); stale mean-curvature-flow
+    state of the earlier matrix must not survive either."""
+    big, small = problems["sphere"], problems["sphere_pad"]
+    assert big.A.nnz > small.A.nnz
+    s = Solver(smoother="wavefront", device=0).set_hierarchy(big.P).precompute(big.A, big.known)
+    s.set_hierarchy(small.P).precompute(small.A, small.known)
+    A2 = small.A.copy()
+    A2.data = A2.data * 1.5
+    # the caller's array has exactly nnz(small) doubles, followed by an inaccessible guard would
+    # be ideal; here: the result must equal a fresh precompute
+    s.update_values(np.ascontiguousarray(A2.data))
+    ora = Oracle(small.P).precompute(A2, small.known)
+    for lv in range(small.nlev):
+        assert np.array_equal(s.matrix(lv, "A").data, ora.matrix(lv, "A").data)
+    with pytest.raises(Exception):
+        s.mcf_step(np.zeros((small.n, 3)))  # no smg_mcf_setup for THIS matrix
+    s.close()
+
+
+def test_too_many_right_hand_sides_are_rejected(problems):
+    pr = problems["sphere_pad"]
+    s = Solver(smoother="multicolour", device=0).set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    k = 33  # SMG_MAX_RHS = 32
+    with pytest.raises(Exception) as e:
+        s.solve(np.zeros((pr.n, k)), np.zeros((pr.n, k)), np.zeros((len(pr.known), k)), 1e-3, 2)
+    assert getattr(e.value, "status", 1) == 1  # SMG_E_INVALID
+    k = 8  # two groups of kMaxK columns still work
+    rng = np.random.default_rng(3)
+    B = np.asfortranarray(rng.standard_normal((pr.n, k)))
+    z, r_his, ok = s.solve(B, np.zeros((pr.n, k), order="F"), np.zeros((len(pr.known), k), order="F"), 1e-9, 40)
+    assert ok
     s.close()
 
 

@@ -1,13 +1,11 @@
 """GPU test of the mean-curvature-flow step with device-side assembly (smg_mcf_setup /
-smg_mcf_step, include/smg.h).  OPT-IN (SMG_RUN_UNVERIFIED=1): the entry points were written in
-round 1 after that round's GPU time was spent and have not run on a GPU yet; their arithmetic
-core is covered on the CPU by tests/test_mcf_core.py.
+smg_mcf_step, include/smg.h); the arithmetic core is also covered on the CPU by
+tests/test_mcf_core.py.
 
 Checks, against the host path the reference takes (assemble M - delta L and M U on the host,
 precompute, solve; 05_example_mean_curvature_flow/main.cpp:66-76): the assembled matrix values
 bit-exact, the step result to 1e-12, several steps in a row, and the CPU checker's result.
 """
-import os
 
 import numpy as np
 import pytest
@@ -18,9 +16,7 @@ from surface_multigrid_code_b200 import meshgen as mg
 from surface_multigrid_code_b200.solver import Solver
 from test_mcf_core import igl_barycentric_mass
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SMG_RUN_UNVERIFIED") != "1",
-                                 reason="not yet verified on a GPU (set SMG_RUN_UNVERIFIED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _mesh():

@@ -159,6 +159,44 @@ def test_file_rendezvous_all_gathers_blobs(tmp_path):
     assert lib.smg_rendezvous_files(b"/nonexistent-dir", b"t", 0, 2, mine[0], nbytes, out, 200) == 1
 
 
+def test_file_rendezvous_ignores_leftovers_of_a_dead_run(tmp_path):
+    """A blob left behind by an earlier run with the same directory and tag (its writer is
+    dead) must never be taken for a peer's blob; blobs are removed once every peer has them."""
+    import ctypes as C
+    import struct
+    import subprocess
+    import sys
+    import threading
+    import time
+
+    lib = _lib.load()
+    nbytes = 64
+    p = subprocess.Popen([sys.executable, "-c", "pass"])
+    p.wait()
+    dead_pid = p.pid
+    magic = 0x534D47525A563032
+    stale = struct.pack("<Qqq", magic, dead_pid, 1) + b"\xee" * nbytes
+    (tmp_path / "job.1").write_bytes(stale)
+    (tmp_path / "job.1.ack").write_bytes(struct.pack("<Qqq", magic, dead_pid, 1) + b"\0" * 32)
+    mine = [b"\x11" * nbytes, b"\x22" * nbytes]
+    got, rcs = [None, None], [None, None]
+
+    def body(r, delay):
+        time.sleep(delay)
+        out = C.create_string_buffer(2 * nbytes)
+        rcs[r] = lib.smg_rendezvous_files(str(tmp_path).encode(), b"job", r, 2, mine[r], nbytes, out, 20000)
+        got[r] = out.raw
+
+    ts = [threading.Thread(target=body, args=(0, 0.0)), threading.Thread(target=body, args=(1, 0.3))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert rcs == [0, 0]
+    assert got[0] == mine[0] + mine[1] and got[1] == mine[0] + mine[1]
+    assert not (tmp_path / "job.0").exists() and not (tmp_path / "job.1").exists()
+
+
 def test_mcf_entry_points_need_a_device(problems):
     pr = problems["mcf"]
     s = Solver(device="none").set_hierarchy(pr.P).precompute(pr.A, None)
