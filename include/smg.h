@@ -75,16 +75,10 @@ typedef struct smg_options {
   int verbose;    /* 1: print the residual per iteration like the reference (cpp:334,349) */
   int locality_reorder; /* 1: order rows inside a phase by a BFS (Cuthill-McKee) rank (default) */
   int sigma;      /* SELL sort window in rows (default 256; 1 = no length sorting) */
-  int tail_rows;  /* levels with at most this many rows (and all coarser ones) run inside one
-                     thread-block cluster with cluster barriers instead of one kernel per
-                     dependent step.  Default 0 = off: on B200 a cluster step that exchanges
-                     data through L2 costs ~4 us against ~2.2 us for a PDL-chained kernel
-                     (profiles/ubench/cluster_step.cu); kept as an experiment */
-  int dataflow;   /* 1: multicolour phases of one relax call synchronise through per-block epoch
-                     flags instead of waiting for the whole previous phase.  Default 0 = off:
-                     measured slower on B200 (a flag hand-off through L2 costs ~3 us against
-                     ~2.2 us for a PDL kernel boundary, and the CTAs of a phase all finish
-                     together, so there is no wavefront to overlap); kept as an experiment */
+  int patch_rows; /* target rows per patch of the communication-avoiding smoother that runs a
+                     whole relax call of a small level in one launch;
+                     0 = automatic, < 0 = off (one kernel per colour phase on every level) */
+  int reserved0;
   int reserved[6];
 } smg_options;
 
@@ -269,11 +263,6 @@ int smg_level_padded_nnz(const smg_handle *h, int lv, int64_t *padded);
  *  [5] padded entries of P by fine row  [6] padded entries of PT by coarse row
  *  [7] smoother phases */
 int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
-
-/* dataflow smoother schedule of level lv, out[4]: [0] row blocks (CTAs per sweep)
- * [1] sum over blocks of the blocks of other phases they wait for [2] the maximum
- * [3] 1 if the dataflow schedule is used on this level */
-int smg_level_dep_stats(const smg_handle *h, int lv, int64_t *out);
 
 /* ---- measurement ----------------------------------------------------------
  * Times `reps` back-to-back launches of one hot-path kernel on level lv with k

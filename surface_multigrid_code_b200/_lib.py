@@ -60,8 +60,8 @@ class smg_options(C.Structure):
         ("verbose", C.c_int),
         ("locality_reorder", C.c_int),
         ("sigma", C.c_int),
-        ("tail_rows", C.c_int),
-        ("dataflow", C.c_int),
+        ("patch_rows", C.c_int),
+        ("reserved0", C.c_int),
         ("reserved", C.c_int * 6),
     ]
 
@@ -116,7 +116,6 @@ SIGNATURES = {
     "smg_get_row_order": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "smg_level_padded_nnz": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_level_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
-    "smg_level_dep_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _ip]),
     "smg_trace_iteration": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip]),
     "smg_launch_count": (C.c_int64, [_vp]),

@@ -579,8 +579,8 @@ sell_gs_phase_multi_kernel(int trace_slot, int row0, int ps, int pe, int nslices
 
 // One phase (colour / wavefront level) of Gauss-Seidel: rows [ps,pe) are mutually
 // independent, so updating them in place and in parallel is exactly the sequential
-// sweep of mg_VCycle.cpp:147-158 restricted to those rows.  Synchronisation with the
-// other phases: see GsFlow (kernels.hpp).
+// sweep of mg_VCycle.cpp:147-158 restricted to those rows.  Phases are separated by
+// kernel boundaries (PDL: the matrix chunk is fetched before the wait).
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int max_chunk,
@@ -590,11 +590,7 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
-  const bool dataflow = flow.mode == 1;
-  // Dataflow: the first launch of a relax call releases its dependents only AFTER its own
-  // PDL wait, so no later launch of the call can run before everything that precedes the
-  // call has completed (and the epoch base in ctrl[0] is final).
-  if (!(dataflow && flow.first)) pdl_launch_dependents();
+  pdl_launch_dependents();
   const int row = row0 + blockIdx.x * kBlock + threadIdx.x;
   const bool active = row >= ps && row < pe;
   const RowView rv = stage_rows<STAGED>((row0 >> 5) + blockIdx.x * kSlices, nslices, row, active,
@@ -614,41 +610,7 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
       }
     }
   }
-  int epoch = 0;
-  if (!dataflow) {
-    pdl_wait();
-  } else {
-    if (flow.first) {
-      pdl_wait();
-      pdl_launch_dependents();
-    }
-    const int base = ld_acquire_gpu(flow.ctrl);
-    const int t = flow.it * flow.np + flow.p;
-    epoch = base + t + 1;
-    if (threadIdx.x < 32) {
-      // wait for the blocks this block reads from / whose readers it overwrites: the most
-      // recent launch of every other phase q (same sweep if q < p, previous sweep otherwise)
-      const int2* dep = flow.dep + (static_cast<size_t>(flow.blk_ofs[flow.p]) + blockIdx.x) * flow.np;
-      for (int q = 0; q < flow.np; q++) {
-        if (q == flow.p) continue;
-        const int tq = (q < flow.p ? flow.it : flow.it - 1) * flow.np + q;
-        if (tq < 0) continue;  // before this call: complete, see above
-        const int need = base + tq + 1;
-        const int2 r = dep[q];
-        const int* fq = flow.flags + flow.blk_ofs[q];
-        for (int j = r.x + (int)threadIdx.x; j <= r.y; j += 32) {
-          int spins = 0;
-          while (ld_acquire_gpu(fq + j) - need < 0) {
-            if (++spins > (1 << 24)) {  // never hang the GPU: flag the error and go on
-              atomicExch(flow.ctrl + 2, 1);
-              break;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
+  pdl_wait();
   stage_wait<STAGED>(&bar);
   if (active) {
     double sum[K];
@@ -659,42 +621,6 @@ sell_gs_phase_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int 
     for (int q = 0; q < K; q++) {
       const size_t o = row + (size_t)q * ld;
       u[o] = __ddiv_rn(__dsub_rn(ld_vec(b + o), sum[q]), d);
-    }
-  }
-  if (dataflow) {
-    __syncthreads();  // every row of the block is written
-    if (threadIdx.x == 0) {
-      __threadfence();
-      st_release_gpu(flow.flags + flow.blk_ofs[flow.p] + blockIdx.x, epoch);
-    }
-    // The middle launches of a call never execute a PDL wait, so their formal completion
-    // is not ordered with anything.  Instead the LAST launch does not complete before every
-    // block of every phase has published its final epoch of this call: "last launch
-    // complete" (what the next kernel's PDL wait sees) then implies "call complete", and
-    // all of the call's writes are visible through the release/acquire chain.
-    if (flow.last) {
-      const int base = epoch - (flow.it * flow.np + flow.p + 1);
-      const int nblk = flow.blk_ofs[flow.np];
-      for (int j = blockIdx.x * kBlock + threadIdx.x; j < nblk; j += gridDim.x * kBlock) {
-        int q = 0;
-        while (q + 1 < flow.np && flow.blk_ofs[q + 1] <= j) q++;
-        const int need = base + (flow.iters - 1) * flow.np + q + 1;
-        int spins = 0;
-        while (ld_acquire_gpu(flow.flags + j) - need < 0) {
-          if (++spins > (1 << 24)) {
-            atomicExch(flow.ctrl + 2, 1);
-            break;
-          }
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(flow.ctrl + 1, 1) == (int)gridDim.x - 1) {  // last block of the call
-          atomicExch(flow.ctrl + 1, 0);
-          atomicAdd(flow.ctrl, flow.iters * flow.np);  // epoch base of the next call
-        }
-      }
     }
   }
   trace_end(trace_slot);
@@ -798,164 +724,6 @@ halo_exchange_kernel(int trace_slot, const XchgPeer* __restrict__ peers, double*
     } else if (atomicAdd(leave, 1) == (int)gridDim.x - 1) {
       atomicExch(leave, 0);
       st_release_gpu(group_epoch, epoch32);
-    }
-  }
-  trace_end(trace_slot);
-}
-
-// ---- cluster tail kernel (see kernels.hpp) --------------------------------------------
-constexpr int kTailThreads = 512;
-constexpr int kTailMaxOps = 96;
-
-__device__ __forceinline__ void cluster_barrier() {
-  // release/acquire at cluster scope: orders the (global-memory) writes of every thread
-  // of the cluster before the reads of every thread that follow the barrier
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ unsigned cluster_nctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-
-// The structure of a row (slice offset, width, columns) is fetched BEFORE the barrier
-// that precedes its step (it is immutable); values, gathers and b are fetched together
-// after it.  kTailRows rows per thread are covered this way; longer steps loop.
-struct TailRow {
-  int w, off;  // off = base + lane
-  int c[kPre];
-};
-
-__device__ __forceinline__ void tail_row_load(TailRow& t, const TailOp& op, int row) {
-  t.w = 0;
-  if (row >= op.pe) return;
-  const int s = row >> 5;
-  const int base = op.slice_ptr[s];
-  t.off = base + (row & 31);
-  t.w = (op.slice_ptr[s + 1] - base) >> 5;
-#pragma unroll
-  for (int j = 0; j < kPre; j++)
-    if (j < t.w) t.c[j] = ld_stream_s32(op.col + t.off + j * 32);
-}
-
-template <int K>
-__device__ __forceinline__ void tail_row_apply(const TailRow& t, const TailOp& op, int row) {
-  const bool gs = op.type == TAIL_GS;
-  double sum[K];
-  double v[kPre];
-  double xv[kPre][K];
-#pragma unroll
-  for (int q = 0; q < K; q++) sum[q] = 0.0;
-#pragma unroll
-  for (int j = 0; j < kPre; j++)
-    if (j < t.w && !(gs && t.c[j] == row)) {
-      v[j] = ld_stream_f64(op.val + t.off + j * 32);
-#pragma unroll
-      for (int q = 0; q < K; q++) xv[j][q] = ld_vec(op.x + t.c[j] + (size_t)q * op.ldx);
-    }
-  double bq[K];
-  double d = 1.0;
-  if (gs) d = ld_stream_f64(op.diag + row);
-  if (op.type != TAIL_RESTRICT_ZERO) {
-    const double* bp = op.type == TAIL_PROLONG_ADD ? op.y : op.b;
-#pragma unroll
-    for (int q = 0; q < K; q++) bq[q] = ld_vec(bp + row + (size_t)q * op.ldy);
-  }
-#pragma unroll
-  for (int j = 0; j < kPre; j++)
-    if (j < t.w && !(gs && t.c[j] == row)) {
-#pragma unroll
-      for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v[j], xv[j][q]));
-    }
-  for (int j = kPre; j < t.w; j++) {  // rows longer than the register window
-    const int c = ld_stream_s32(op.col + t.off + j * 32);
-    const double vv = ld_stream_f64(op.val + t.off + j * 32);
-    if (gs && c == row) continue;
-#pragma unroll
-    for (int q = 0; q < K; q++)
-      sum[q] = __dadd_rn(sum[q], __dmul_rn(vv, ld_vec(op.x + c + (size_t)q * op.ldx)));
-  }
-#pragma unroll
-  for (int q = 0; q < K; q++) {
-    const size_t o = row + (size_t)q * op.ldy;
-    switch (op.type) {
-      case TAIL_GS: op.y[o] = __ddiv_rn(__dsub_rn(bq[q], sum[q]), d); break;
-      case TAIL_RESIDUAL: op.y[o] = __dsub_rn(bq[q], sum[q]); break;
-      case TAIL_RESTRICT_ZERO:
-        op.y[o] = sum[q];
-        op.z[o] = 0.0;
-        break;
-      default: op.y[o] = __dadd_rn(bq[q], sum[q]); break;
-    }
-  }
-}
-
-template <int K>
-__global__ void __launch_bounds__(kTailThreads, 1)
-tail_kernel(int trace_slot, const TailOp* __restrict__ ops, int nops) {
-  trace_begin(trace_slot);
-  pdl_launch_dependents();
-  __shared__ TailOp sops[kTailMaxOps];
-  {  // the op list is immutable: stage it (and the first rows' structure) before the PDL wait
-    const int words = nops * (int)(sizeof(TailOp) / sizeof(int));
-    const int* src = reinterpret_cast<const int*>(ops);
-    int* dst = reinterpret_cast<int*>(sops);
-    for (int i = threadIdx.x; i < words; i += kTailThreads) dst[i] = src[i];
-  }
-  __syncthreads();
-  // The tail's matrices were last touched one V-cycle leg ago and have usually left L2:
-  // ask for all of them at once (TMA bulk prefetch into L2, one op per CTA round-robin)
-  // so that the dependent steps below pay L2 latency, not DRAM latency.
-  if (threadIdx.x < 32) {
-    for (int i = cluster_ctarank() * 32 + threadIdx.x; i < nops * 3; i += cluster_nctarank() * 32) {
-      const TailOp& op = sops[i / 3];
-      const int part = i % 3;
-      const char* p = nullptr;
-      size_t bytes = 0;
-      if (part == 0) {
-        p = reinterpret_cast<const char*>(op.val + op.ent0);
-        bytes = static_cast<size_t>(op.ent1 - op.ent0) * 8;
-      } else if (part == 1) {
-        p = reinterpret_cast<const char*>(op.col + op.ent0);
-        bytes = static_cast<size_t>(op.ent1 - op.ent0) * 4;
-      } else if (op.type == TAIL_GS) {
-        p = reinterpret_cast<const char*>(op.diag + (op.ps & ~1));
-        bytes = (static_cast<size_t>(op.pe - (op.ps & ~1)) * 8 + 15) & ~static_cast<size_t>(15);
-      }
-      if (bytes > 0)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p),
-                     "r"(static_cast<uint32_t>(bytes))
-                     : "memory");
-    }
-  }
-  const int gtid = cluster_ctarank() * kTailThreads + threadIdx.x;
-  const int nthreads = cluster_nctarank() * kTailThreads;
-  constexpr int kTailRows = K == 1 ? 3 : 2;
-  TailRow cur[kTailRows];
-#pragma unroll
-  for (int t = 0; t < kTailRows; t++) tail_row_load(cur[t], sops[0], sops[0].ps + gtid + t * nthreads);
-  pdl_wait();
-  for (int i = 0; i < nops; i++) {
-    const TailOp& op = sops[i];
-    int row = op.ps + gtid;
-#pragma unroll
-    for (int t = 0; t < kTailRows; t++, row += nthreads)
-      if (row < op.pe) tail_row_apply<K>(cur[t], op, row);
-    for (; row < op.pe; row += nthreads) {
-      tail_row_load(cur[0], op, row);
-      tail_row_apply<K>(cur[0], op, row);
-    }
-    if (i + 1 < nops) {  // the next step's structure is fetched while the barrier completes
-#pragma unroll
-      for (int t = 0; t < kTailRows; t++)
-        tail_row_load(cur[t], sops[i + 1], sops[i + 1].ps + gtid + t * nthreads);
-      cluster_barrier();
     }
   }
   trace_end(trace_slot);
@@ -1151,7 +919,7 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
   if (pe <= ps) return;
   const int row0 = ps & ~31;
   // large phases: R rows per thread (fewer, fatter CTAs)
-  if (g_gs_rows > 1 && flow.mode == 0 && g_use_tma && k == 1 && M.max_width <= kPre &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre &&
       pe - row0 >= 150000) {  // at least one full wave of fat CTAs
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     const int R = g_gs_rows;
@@ -1290,56 +1058,6 @@ __global__ void symmetrize_lower_kernel(double* D, int n) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y * blockDim.y + threadIdx.y;
   if (r < n && c < n && r > c) D[(size_t)c + (size_t)r * n] = D[(size_t)r + (size_t)c * n];
-}
-
-// u(i,:) += sum_j Ainv(i,j) b(j,:) ; one warp per row, Ainv symmetric so row i is
-// read as the contiguous column i.
-template <int K>
-__global__ void __launch_bounds__(kBlock)
-dense_symv_add_kernel(int trace_slot, const double* __restrict__ Ainv, const double* b, double* u,
-                      int n) {
-  trace_begin(trace_slot);
-  pdl_launch_dependents();
-  const int i = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  // the inverse is immutable during a solve: the first chunk of the row is fetched
-  // before the PDL wait
-  constexpr int kAhead = 4;
-  double ahead[kAhead];
-  const double* a = Ainv + (size_t)(i < n ? i : 0) * n;
-#pragma unroll
-  for (int t = 0; t < kAhead; t++) {
-    const int j = lane + 32 * t;
-    ahead[t] = (i < n && j < n) ? ld_stream_f64(a + j) : 0.0;
-  }
-  pdl_wait();
-  if (i >= n) {
-    trace_end(trace_slot);
-    return;
-  }
-  double acc[K];
-#pragma unroll
-  for (int q = 0; q < K; q++) acc[q] = 0.0;
-#pragma unroll
-  for (int t = 0; t < kAhead; t++) {
-    const int j = lane + 32 * t;
-    if (j < n) {
-#pragma unroll
-      for (int q = 0; q < K; q++) acc[q] += ahead[t] * ld_vec(b + j + (size_t)q * n);
-    }
-  }
-  for (int j = lane + 32 * kAhead; j < n; j += 32) {
-    const double aij = ld_stream_f64(a + j);
-#pragma unroll
-    for (int q = 0; q < K; q++) acc[q] += aij * ld_vec(b + j + (size_t)q * n);
-  }
-#pragma unroll
-  for (int q = 0; q < K; q++) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_down_sync(0xffffffffu, acc[q], o);
-    if (lane == 0) u[i + (size_t)q * n] = ld_vec(u + i + (size_t)q * n) + acc[q];
-  }
-  trace_end(trace_slot);
 }
 
 // ---- coarse direct solve: u += Ainv * b with Ainv symmetric -----------------------
@@ -1583,67 +1301,6 @@ void launch_symmetrize_lower(double* D, int n, cudaStream_t st) {
   dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8);
   symmetrize_lower_kernel<<<g, b, 0, st>>>(D, n);
 }
-namespace {
-template <int K>
-int tail_cluster_size_for() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  cached = 0;
-  cudaFuncSetAttribute(tail_kernel<K>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  for (int cs : {16, 8, 4, 2, 1}) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs);
-    cfg.blockDim = dim3(kTailThreads);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, tail_kernel<K>, &cfg) == cudaSuccess &&
-        nclusters >= 1) {
-      cached = cs;
-      break;
-    }
-    cudaGetLastError();
-  }
-  return cached;
-}
-
-template <int K>
-void launch_tail_k(const TailOp* d_ops, int nops, int cluster_size, cudaStream_t st) {
-  int slot = -1;
-  if (g_trace.on && g_trace.next < g_trace.cap) {
-    slot = g_trace.next++;
-    g_trace.names.push_back(g_trace.label + " tail_kernel ops" + std::to_string(nops));
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cluster_size);
-  cfg.blockDim = dim3(kTailThreads);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_size;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, tail_kernel<K>, slot, d_ops, nops);
-}
-}  // namespace
-
-int tail_cluster_size() { return tail_cluster_size_for<1>(); }
-int tail_max_ops() { return kTailMaxOps; }
-
-void launch_tail(const TailOp* d_ops, int nops, int k, int cluster_size, cudaStream_t st) {
-  if (nops <= 0) return;
-  SMG_DISPATCH_K(k, (tail_cluster_size_for<K>(), launch_tail_k<K>(d_ops, nops, cluster_size, st)));
-}
-
 size_t dense_sym_scratch_doubles(int n, int k) {
   const int nblk = (n + kTile - 1) / kTile;
   return static_cast<size_t>(nblk) * (k < kMaxK ? k : kMaxK) * n;
@@ -1666,12 +1323,6 @@ void launch_pack_sym_tiles(const double* A_lower, double* tiles, int n, cudaStre
   if (n <= 0) return;
   const int nblk = (n + kTile - 1) / kTile;
   pack_sym_tiles_kernel<<<nblk * (nblk + 1) / 2, 256, 0, st>>>(A_lower, tiles, n);
-}
-void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
-                           cudaStream_t st) {
-  if (n <= 0) return;
-  const int g = blocks_for(n, kBlock / 32);
-  SMG_DISPATCH_K(k, launch_kernel("coarse_symv", dense_symv_add_kernel<K>, g, kBlock, 0, st, Ainv, b, u, n));
 }
 void launch_gather_system(const double* RHS, const double* z0, const double* kv, int n_full,
                           int n_known, const int* g, const int* auk_ptr, const int* auk_q,

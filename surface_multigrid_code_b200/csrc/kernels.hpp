@@ -59,32 +59,6 @@ void set_pdl_enabled(bool on);
 void set_tma_enabled(bool on);
 // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2 or 4)
 void set_gs_rows(int r);
-// ---- cluster "tail" kernel ---------------------------------------------------------
-// Levels too small to fill the GPU are latency-bound: a chain of per-phase kernels
-// costs ~2 us per dependent step.  The tail kernel runs a whole list of such steps
-// (Gauss-Seidel phases, residual, restrict, prolong-add of several levels) inside ONE
-// thread-block cluster, separated by cluster barriers (~0.2 us) instead of kernel
-// boundaries.  One op = one dependent step over rows [ps, pe) of a SELL matrix.
-enum TailOpType { TAIL_GS = 0, TAIL_RESIDUAL = 1, TAIL_RESTRICT_ZERO = 2, TAIL_PROLONG_ADD = 3 };
-struct TailOp {
-  int type = 0;
-  int ps = 0, pe = 0;  // rows of M handled by this step
-  int ldx = 0, ldy = 0;
-  int ent0 = 0, ent1 = 0;  // stored entries [ent0, ent1) of col / val belong to rows [ps, pe)
-  const int* slice_ptr = nullptr;
-  const int* col = nullptr;
-  const double* val = nullptr;
-  const double* diag = nullptr;  // TAIL_GS
-  const double* x = nullptr;     // gathered vector (GS: == y)
-  const double* b = nullptr;     // TAIL_GS, TAIL_RESIDUAL
-  double* y = nullptr;           // written vector
-  double* z = nullptr;           // TAIL_RESTRICT_ZERO: zeroed vector
-};
-// cluster size the device accepts for the tail kernel (16, 8, ... or 0 = unsupported)
-int tail_cluster_size();
-int tail_max_ops();
-void launch_tail(const TailOp* d_ops, int nops, int k, int cluster_size, cudaStream_t st);
-
 // in-kernel timeline: slots of 2 x u64 [min start, max end] in nanoseconds (%globaltimer);
 // the caller initialises the buffer to {~0, 0} per slot
 void trace_start(unsigned long long* dev_buf, int cap);
@@ -102,23 +76,9 @@ void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, i
 int residual_norm_blocks(int nrows);
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
                            double* scratch, double* out, cudaStream_t st);
-// Dataflow schedule of the smoother.  mode 0: every phase kernel waits (PDL) for the whole
-// previous phase.  mode 1: only the first phase kernel of a relax call waits for its
-// predecessor; inside the call a 256-row block waits just for the blocks of the other
-// phases whose rows it reads (or whose readers it would overwrite), through per-block
-// epoch flags in global memory, so consecutive phases overlap like a wavefront instead of
-// draining the GPU at every colour change.
+// Per-launch extras of a Gauss-Seidel phase kernel.
 struct GsFlow {
-  int mode = 0;
-  int np = 0;               // phases per sweep
-  int p = 0, it = 0;        // this launch: phase p of sweep it
-  int iters = 0;            // sweeps of this relax call
-  int first = 0, last = 0;  // first / last (non-empty) launch of the call
-  const int2* dep = nullptr;     // [(blk_ofs[p] + b) * np + q] = {lo, hi} blocks of phase q
-  const int* blk_ofs = nullptr;  // np + 1
-  int* flags = nullptr;          // epoch per block
-  int* ctrl = nullptr;           // [0] epoch base, [1] finished blocks of the last launch, [2] error
-  // L2 prefetch of the NEXT launch's matrix chunk (both modes): CTA b asks for the slices
+  // L2 prefetch of the NEXT launch's matrix chunk: CTA b asks for the slices
   // [pf_slice0 + 8 b, pf_slice0 + 8 b + 8) clipped to pf_slice_end; pf_slice0 < 0: none
   int pf_slice0 = -1, pf_slice_end = 0;
 };
@@ -191,9 +151,6 @@ size_t dense_sym_tiles_doubles(int n);
 void launch_pack_sym_tiles(const double* A_lower, double* tiles, int n, cudaStream_t st);
 void launch_dense_sym_add(const double* tiles, const double* b, double* u, double* scratch, int n,
                           int k, cudaStream_t st);
-// u = u + Ainv * b  (Ainv symmetric dense n x n; b,u: n x k), one warp per full row
-void launch_dense_symv_add(const double* Ainv, const double* b, double* u, int n, int k,
-                           cudaStream_t st);
 
 // ---- mean-curvature-flow step: device-side assembly (05_example_mean_curvature_flow/main.cpp:66-69)
 // dblA (nF), mass (nV) are scratch; a_val receives M - delta * L in the CSC order of

@@ -486,7 +486,6 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
     L.order = make_row_order(A, grp, L.nparts * L.n_phases, rank, opt.sigma);
     L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
     remap_src(L.sellA, L.live_src);
-    L.blk_ofs.assign(1, 0);  // no dataflow schedule
     return;
   }
   L.layout = LAYOUT_PLAIN;
@@ -496,53 +495,6 @@ static void plan_level_layout(LevelPlan& L, const PlanOptions& opt) {
   L.sellA = build_sell(A, L.order.perm, L.order.iperm, opt.sort_cols > 0);
   remap_src(L.sellA, L.live_src);
   st.lap("  build SELL A");
-  // block dependency ranges for the dataflow smoother
-  const int np = L.n_phases;
-  L.blk_ofs.assign(static_cast<size_t>(np) + 1, 0);
-  std::vector<int> row0(np, 0);
-  for (int p = 0; p < np; p++) {
-    const int ps = L.order.phase_ptr[p], pe = L.order.phase_ptr[p + 1];
-    row0[p] = ps & ~(kSliceRows - 1);
-    const int nb = pe > ps ? (pe - row0[p] + kBlockRows - 1) / kBlockRows : 0;
-    L.blk_ofs[p + 1] = L.blk_ofs[p] + nb;
-  }
-  const int nblk = L.blk_ofs[np];
-  if (np <= 16 && opt.dataflow) {
-    L.dep_lo.assign(static_cast<size_t>(nblk) * np, 1);
-    L.dep_hi.assign(static_cast<size_t>(nblk) * np, 0);
-    for (int r = 0; r < n; r++) {  // r: permuted row
-      const int p = L.phase[L.order.perm[r]];
-      const int blk = L.blk_ofs[p] + (r - row0[p]) / kBlockRows;
-      const int v = L.order.perm[r];
-      for (int e = A.colptr[v]; e < A.colptr[v + 1]; e++) {
-        const int w = A.rowidx[e];
-        if (w == v) continue;
-        const int q = L.phase[w];
-        const int bq = (L.order.iperm[w] - row0[q]) / kBlockRows;
-        int& lo = L.dep_lo[static_cast<size_t>(blk) * np + q];
-        int& hi = L.dep_hi[static_cast<size_t>(blk) * np + q];
-        if (lo > hi) lo = hi = bq;
-        else {
-          lo = std::min(lo, bq);
-          hi = std::max(hi, bq);
-        }
-      }
-    }
-    if (std::getenv("SMG_DEBUG_DEPS")) {
-      for (int b = 0; b < nblk; b++) {
-        int c = 0;
-        for (int q = 0; q < np; q++)
-          if (L.dep_hi[(size_t)b * np + q] >= L.dep_lo[(size_t)b * np + q])
-            c += L.dep_hi[(size_t)b * np + q] - L.dep_lo[(size_t)b * np + q] + 1;
-        if (c > 24) {
-          std::fprintf(stderr, "blk %d/%d deps %d :", b, nblk, c);
-          for (int q = 0; q < np; q++)
-            std::fprintf(stderr, " [%d,%d]", L.dep_lo[(size_t)b * np + q], L.dep_hi[(size_t)b * np + q]);
-          std::fprintf(stderr, "\n");
-        }
-      }
-    }
-  }
 }
 
 // ---- multi-GPU exchange lists ---------------------------------------------------------

@@ -125,12 +125,6 @@ struct LevelPlan {
   std::vector<int> phase;     // per row (reference numbering)
   RowOrder order;
   Sell sellA;
-  // Dataflow smoother schedule (multicolour mode): phase p is processed in blocks of
-  // kBlockRows rows starting at (phase_ptr[p] & ~31).  Block b of phase p reads rows of
-  // the blocks [dep_lo, dep_hi] of every other phase q:
-  //   dep[(blk_ofs[p] + b) * n_phases + q] = {lo, hi}  (lo > hi: none)
-  std::vector<int> blk_ofs;           // n_phases + 1
-  std::vector<int> dep_lo, dep_hi;    // n_blocks * n_phases
   // lv >= 1 (operators between level lv-1 (fine) and lv (coarse)):
   Csc P, PT;                  // with values, as the reference leaves mg[lv].P / .PT
   bool pruned = false;
@@ -163,7 +157,6 @@ struct PlanOptions {
   int locality_reorder = 1;
   int sigma = 256;
   int sort_cols = -1;  // -1: on for multicolour, off for wavefront (bit-parity order)
-  int dataflow = 0;    // 1: also plan the block dependency ranges of the dataflow smoother
   // multi-GPU: number of ranks the fine levels are partitioned over, and how many levels
   // (from level 0) are partitioned; < 0: every level with at least dist_min_rows rows per
   // rank (always level 0, never the coarsest)

@@ -144,10 +144,6 @@ struct LevelDev {
   DevBuf<double> diag;  // permuted numbering
   DevBuf<int> perm;     // new -> old
   std::vector<int> phase_ptr;
-  // dataflow smoother (kernels.hpp::GsFlow)
-  bool dataflow = false;
-  DevBuf<int2> dep;
-  DevBuf<int> blk_ofs, flags, ctrl;
   // transfer operators between level l-1 (fine) and l (coarse), l >= 1
   SellBufs sellP, sellPT;
   DevBuf<int> p_colptr, p_rowidx, pt_colptr, pt_rowidx;  // CSC of P and of PT
@@ -228,11 +224,6 @@ struct DistBlob {  // what smg_dist_get_handle exports (smg_dist_handle_bytes() 
   char uuid[16];  // of the device: two ranks on one physical GPU are detected by it
 };
 
-struct TailLists {
-  DevBuf<smg::TailOp> down, up;
-  int n_down = 0, n_up = 0;
-};
-
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;
@@ -277,9 +268,6 @@ struct smg_handle {
   DevBuf<double> flush;      // L2 flush buffer for smg_time_kernel
 
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
-  // cluster tail kernel: first level handled by it (== number of levels - 1: none)
-  int tail_cluster = 0, tail_start = 0;
-  std::map<std::tuple<int, int, int, int, int>, TailLists> tails;  // (first level, pre, post, k0, kk)
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // mean-curvature-flow assembly (smg_mcf_*)
@@ -329,109 +317,6 @@ void drop_graphs(smg_handle* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   h->graphs.clear();
-  h->tails.clear();  // the op lists hold pointers into the work vectors
-}
-
-// first level of the V-cycle started at lv0 that runs inside the cluster tail kernel
-int tail_first_level(const smg_handle* h, int lv0) {
-  const int last = static_cast<int>(h->lv.size()) - 1;
-  if (h->tail_cluster <= 0 || h->opt.tail_rows <= 0 || dist_on(h)) return last;
-  return std::min(last, std::max(lv0, h->tail_start));
-}
-
-smg::TailOp make_op(int type, const SellDev& M, const smg::Sell& host, const double* val, int ps,
-                    int pe) {
-  smg::TailOp op;
-  op.type = type;
-  op.ps = ps;
-  op.pe = pe;
-  op.ent0 = host.slice_ptr[ps >> 5];
-  op.ent1 = host.slice_ptr[std::min(host.nslices, (pe + 31) >> 5)];
-  op.slice_ptr = M.slice_ptr;
-  op.col = M.col;
-  op.val = val;
-  return op;
-}
-
-// op lists of the two legs of the tail (levels ts .. last-1) for columns [k0, k0+kk)
-int prepare_tail(smg_handle* h, int lv0, int pre, int post, int k0, int kk) {
-  const int last = static_cast<int>(h->lv.size()) - 1;
-  const int ts = tail_first_level(h, lv0);
-  if (ts >= last) return SMG_OK;
-  const auto key = std::make_tuple(ts, pre, post, k0, kk);
-  if (h->tails.count(key)) return SMG_OK;
-  std::vector<smg::TailOp> down, up;
-  auto gs_ops = [&](std::vector<smg::TailOp>& out, int l, int iters) {
-    LevelDev& L = h->lv[l];
-    const SellDev A = L.sellA.view();
-    const size_t o = static_cast<size_t>(k0) * L.n;
-    for (int it = 0; it < iters; it++)
-      for (size_t p = 0; p + 1 < L.phase_ptr.size(); p++) {
-        if (L.phase_ptr[p + 1] <= L.phase_ptr[p]) continue;
-        smg::TailOp op = make_op(smg::TAIL_GS, A, h->plan.lv[l].sellA, A.val, L.phase_ptr[p],
-                                 L.phase_ptr[p + 1]);
-        op.diag = L.diag.p;
-        op.x = L.u.p + o;
-        op.b = L.b.p + o;
-        op.y = L.u.p + o;
-        op.ldx = op.ldy = L.n;
-        out.push_back(op);
-      }
-  };
-  for (int l = ts; l < last; l++) {
-    LevelDev& L = h->lv[l];
-    LevelDev& C = h->lv[l + 1];
-    const size_t o = static_cast<size_t>(k0) * L.n, oc = static_cast<size_t>(k0) * C.n;
-    gs_ops(down, l, pre);
-    if (L.n > 0) {
-      const SellDev A = L.sellA.view();
-      smg::TailOp op = make_op(smg::TAIL_RESIDUAL, A, h->plan.lv[l].sellA, A.valT, 0, L.n);
-      op.x = L.u.p + o;
-      op.b = L.b.p + o;
-      op.y = L.r.p + o;
-      op.ldx = op.ldy = L.n;
-      down.push_back(op);
-    }
-    if (C.n > 0) {
-      const SellDev PT = C.sellPT.view();
-      smg::TailOp op = make_op(smg::TAIL_RESTRICT_ZERO, PT, h->plan.lv[l + 1].sellPT, PT.val, 0, C.n);
-      op.x = L.r.p + o;
-      op.ldx = L.n;
-      op.y = C.b.p + oc;
-      op.z = C.u.p + oc;
-      op.ldy = C.n;
-      down.push_back(op);
-    }
-  }
-  for (int l = last - 1; l >= ts; l--) {
-    LevelDev& L = h->lv[l];
-    LevelDev& C = h->lv[l + 1];
-    if (L.n > 0) {
-      const SellDev P = C.sellP.view();
-      smg::TailOp op = make_op(smg::TAIL_PROLONG_ADD, P, h->plan.lv[l + 1].sellP, P.val, 0, L.n);
-      op.x = C.u.p + static_cast<size_t>(k0) * C.n;
-      op.ldx = C.n;
-      op.y = L.u.p + static_cast<size_t>(k0) * L.n;
-      op.ldy = L.n;
-      up.push_back(op);
-    }
-    gs_ops(up, l, post);
-  }
-  TailLists& T = h->tails[key];
-  T.n_down = static_cast<int>(down.size());
-  T.n_up = static_cast<int>(up.size());
-  SMG_CUDA(h, T.down.upload(down, h->stream));
-  SMG_CUDA(h, T.up.upload(up, h->stream));
-  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
-  return SMG_OK;
-}
-
-void launch_tail_leg(smg_handle* h, const DevBuf<smg::TailOp>& ops, int n, int kk) {
-  const int cap = smg::tail_max_ops();
-  for (int i = 0; i < n; i += cap) {  // long op lists (wavefront schedules) go out in pieces
-    smg::launch_tail(ops.p + i, std::min(cap, n - i), kk, h->tail_cluster, h->stream);
-    h->launches++;
-  }
 }
 
 int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT) {
@@ -615,13 +500,6 @@ void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, i
     }
   if (iters <= 0 || (p_first < 0 && !part)) return;
   smg::GsFlow flow;
-  flow.mode = L.dataflow && (p_last > p_first || iters > 1) ? 1 : 0;
-  flow.np = np;
-  flow.iters = iters;
-  flow.dep = L.dep.p;
-  flow.blk_ofs = L.blk_ofs.p;
-  flow.flags = L.flags.p;
-  flow.ctrl = L.ctrl.p;
   // the columns of a block of right-hand sides are independent: one complete relax call
   // (its own epoch range) per group of kMaxK columns
   for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
@@ -631,13 +509,9 @@ void relax_device(smg_handle* h, int l, int iters, const double* b, double* u, i
       for (int p = 0; p < np; p++) {
         const int ps = L.gs_ranges[p].first, pe = L.gs_ranges[p].second;
         if (pe > ps) {
-          flow.p = p;
-          flow.it = it;
-          flow.first = it == 0 && p == p_first;
-          flow.last = it == iters - 1 && p == p_last;
           // next non-empty phase of this call (its matrix chunk is prefetched into L2)
           flow.pf_slice0 = -1;
-          if (!flow.last && !h->no_prefetch) {
+          if (!(it == iters - 1 && p == p_last) && !h->no_prefetch) {
             int q = p;
             do q = (q + 1) % np; while (L.gs_ranges[q].second <= L.gs_ranges[q].first);
             flow.pf_slice0 = L.gs_ranges[q].first >> 5;
@@ -763,9 +637,8 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
 // work vectors lv[l].b / .u of levels l >= lv0.
 void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
   const int last = static_cast<int>(h->lv.size()) - 1;
-  const int ts = tail_first_level(h, lv0);
   char label[32];
-  for (int l = lv0; l < ts; l++) {
+  for (int l = lv0; l < last; l++) {
     LevelDev& L = h->lv[l];
     LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d down", l);
@@ -775,28 +648,10 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     if (dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED) exchange(h, L.x_halo_r, L.r.p, L.n, k);
     restrict_device(h, l, L.r.p, C.b.p, k, C.u.p);         // :44 and uc = 0 (:46-47), fused
   }
-  if (ts < last) {  // levels ts .. last-1, down leg, inside one cluster
-    std::snprintf(label, sizeof(label), "L%d-%d down", ts, last - 1);
-    smg::trace_label(label);
-    for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
-      const int kk = std::min(smg::kMaxK, k - k0);
-      const TailLists& T = h->tails.at(std::make_tuple(ts, pre, post, k0, kk));
-      launch_tail_leg(h, T.down, T.n_down, kk);
-    }
-  }
   std::snprintf(label, sizeof(label), "L%d", last);
   smg::trace_label(label);
   coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
-  if (ts < last) {
-    std::snprintf(label, sizeof(label), "L%d-%d up", ts, last - 1);
-    smg::trace_label(label);
-    for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
-      const int kk = std::min(smg::kMaxK, k - k0);
-      const TailLists& T = h->tails.at(std::make_tuple(ts, pre, post, k0, kk));
-      launch_tail_leg(h, T.up, T.n_up, kk);
-    }
-  }
-  for (int l = ts - 1; l >= lv0; l--) {
+  for (int l = last - 1; l >= lv0; l--) {
     LevelDev& L = h->lv[l];
     std::snprintf(label, sizeof(label), "L%d up", l);
     smg::trace_label(label);
@@ -806,8 +661,6 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
 }
 
 int vcycle_run(smg_handle* h, int lv0, int pre, int post, int k) {
-  for (int k0 = 0; k0 < k; k0 += smg::kMaxK)
-    SMG_TRY(prepare_tail(h, lv0, pre, post, k0, std::min(smg::kMaxK, k - k0)));
   if (!h->opt.use_graph) {
     vcycle_device(h, lv0, pre, post, k);
     return check_launch(h, "vcycle");
@@ -993,17 +846,6 @@ int upload_plan(smg_handle* h) {
     SMG_CUDA(h, L.diag.alloc(static_cast<size_t>(P.n)));
     SMG_CUDA(h, L.perm.upload(P.order.perm, st));
     L.phase_ptr = P.order.phase_ptr;
-    L.dataflow = !dist_on(h) && h->opt.dataflow && h->opt.smoother == SMG_SMOOTHER_MULTICOLOUR && P.n_phases >= 2 &&
-                 !P.dep_lo.empty();
-    if (L.dataflow) {
-      std::vector<int2> dep(P.dep_lo.size());
-      for (size_t i = 0; i < dep.size(); i++) dep[i] = make_int2(P.dep_lo[i], P.dep_hi[i]);
-      SMG_CUDA(h, L.dep.upload(dep, st));
-      SMG_CUDA(h, L.blk_ofs.upload(P.blk_ofs, st));
-      SMG_CUDA(h, L.flags.upload(std::vector<int>(static_cast<size_t>(P.blk_ofs.back()), 0), st));
-      SMG_CUDA(h, L.ctrl.upload(std::vector<int>(4, 0), st));
-      SMG_CUDA(h, cudaStreamSynchronize(st));  // the temporaries above go out of scope
-    }
     if (l >= 1) {
       SMG_TRY(upload_sell(h, P.sellP, &L.sellP, false));
       SMG_TRY(upload_sell(h, P.sellPT, &L.sellPT, false));
@@ -1026,8 +868,6 @@ int upload_plan(smg_handle* h) {
       h->launches += 2;
     }
   }
-  h->tail_start = nlev - 1;
-  for (int l = nlev - 2; l >= 0 && pl.lv[l].n <= h->opt.tail_rows; l--) h->tail_start = l;
   SMG_CUDA(h, h->lhs_src.upload(pl.lhs_src, st));
   // permuted unknown row -> caller index
   const std::vector<int>& perm0 = pl.lv[0].order.perm;
@@ -1166,24 +1006,6 @@ int valid_level(smg_handle* h, int lv, bool need_coarser) {
   return SMG_OK;
 }
 
-// a dataflow wait that timed out leaves ctrl[2] != 0 on its level
-int check_dataflow(smg_handle* h) {
-  int* flags = reinterpret_cast<int*>(h->h_norm + 32);  // pinned scratch
-  int n = 0;
-  for (auto& L : h->lv)
-    if (L.dataflow && n < 32) {
-      flags[n] = 0;
-      SMG_CUDA(h, cudaMemcpyAsync(flags + n, L.ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      n++;
-    }
-  if (n == 0) return SMG_OK;
-  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
-  int bad = 0;
-  for (int i = 0; i < n; i++) bad |= flags[i];
-  if (bad) return fail(h, SMG_E_INTERNAL, "dataflow smoother: a device-side wait timed out");
-  return SMG_OK;
-}
-
 // multi-GPU: a level vector whose rows were computed by their owners only -> complete on
 // every rank (collective)
 void complete_rows(smg_handle* h, int l, double* vec, int k) {
@@ -1231,7 +1053,6 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
     h->launches++;
   }
   SMG_TRY(check_launch(h, "solve"));
-  SMG_TRY(check_dataflow(h));
   SMG_TRY(check_exchange(h));
   *n_his = nh;
   *converged = residual > tol ? 0 : 1;  // cpp:357-360 (stale residual, by design)
@@ -1280,8 +1101,7 @@ void smg_default_options(smg_options* opt) {
   opt->verbose = 0;
   opt->locality_reorder = 1;
   opt->sigma = 256;
-  opt->dataflow = 0;  // measured slower than phase barriers on B200, see DESIGN.md section 4
-  opt->tail_rows = 0;  // measured slower than the PDL kernel chain on B200, see DESIGN.md section 4
+  opt->patch_rows = 0;  // automatic
 }
 
 int smg_version(void) { return SMG_VERSION; }
@@ -1341,9 +1161,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
   if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
   if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->no_prefetch = (e[0] && e[0] != '0');
-  if (const char* e = std::getenv("SMG_DATAFLOW")) h->opt.dataflow = (e[0] && e[0] != '0');
-  if (const char* e = std::getenv("SMG_TAIL_ROWS")) h->opt.tail_rows = std::atoi(e);
-  h->tail_cluster = h->opt.tail_rows > 0 ? smg::tail_cluster_size() : 0;
+  if (const char* e = std::getenv("SMG_PATCH_ROWS")) h->opt.patch_rows = std::atoi(e);
   if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 1024 * sizeof(double)) != cudaSuccess) {
@@ -1448,7 +1266,6 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   po.smoother = h->opt.smoother;
   po.locality_reorder = h->opt.locality_reorder;
   po.sigma = h->opt.sigma > 0 ? h->opt.sigma : 1;
-  po.dataflow = h->opt.dataflow || h->plan_only;  // (plan-only handles report the schedule statistics)
   po.world = h->dist.world;
   po.dist_levels = h->dist_levels;
   if (h->dist_min_rows > 0) po.dist_min_rows = h->dist_min_rows;
@@ -2179,30 +1996,6 @@ int smg_level_stats(const smg_handle* h, int lv, int64_t* out) {
   return SMG_OK;
 }
 
-int smg_level_dep_stats(const smg_handle* h, int lv, int64_t* out) {
-  SMG_TRY(check_ready(h, false));
-  if (lv < 0 || lv >= static_cast<int>(h->plan.lv.size()) || !out) return SMG_E_INVALID;
-  const smg::LevelPlan& L = h->plan.lv[lv];
-  const int np = L.n_phases;
-  const int64_t nblk = L.blk_ofs.empty() ? 0 : L.blk_ofs.back();
-  int64_t tot = 0, mx = 0;
-  if (!L.dep_lo.empty())
-    for (int64_t b = 0; b < nblk; b++) {
-      int64_t c = 0;
-      for (int q = 0; q < np; q++) {
-        const int lo = L.dep_lo[b * np + q], hi = L.dep_hi[b * np + q];
-        if (hi >= lo) c += hi - lo + 1;
-      }
-      tot += c;
-      mx = std::max(mx, c);
-    }
-  out[0] = nblk;
-  out[1] = tot;
-  out[2] = mx;
-  out[3] = 0;
-  return SMG_OK;
-}
-
 // ---- measurement -----------------------------------------------------------------
 int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush_l2,
                     float* ms_per_rep, int* launches_per_rep) {
@@ -2297,8 +2090,6 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
   SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
   SMG_CUDA(h, h->norm_out.reserve(4));
   if (dist_on(h)) SMG_CUDA(h, h->dist.normv.reserve(static_cast<size_t>(h->dist.world) * 16));
-  for (int k0 = 0; k0 < k; k0 += smg::kMaxK)
-    SMG_TRY(prepare_tail(h, 0, h->opt.pre_relax, h->opt.post_relax, k0, std::min(smg::kMaxK, k - k0)));
   smg::trace_start(buf.p, max_events);
   smg::trace_label("norm");
   cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);

@@ -63,8 +63,7 @@ class Solver:
 
     def __init__(self, smoother: str = "multicolour", device=None, use_graph: bool = True,
                  pre_relax: int = 2, post_relax: int = 2, verbose: bool = False,
-                 locality_reorder: bool = True, sigma: int = 256, tail_rows: Optional[int] = None,
-                 dataflow: Optional[bool] = None):
+                 locality_reorder: bool = True, sigma: int = 256, patch_rows: Optional[int] = None):
         self._lib = L.load()
         opt = L.smg_options()
         self._lib.smg_default_options(C.byref(opt))
@@ -82,10 +81,8 @@ class Solver:
         opt.verbose = int(bool(verbose))
         opt.locality_reorder = int(bool(locality_reorder))
         opt.sigma = int(sigma)
-        if tail_rows is not None:
-            opt.tail_rows = int(tail_rows)
-        if dataflow is not None:
-            opt.dataflow = int(bool(dataflow))
+        if patch_rows is not None:  # 0 automatic, < 0 off
+            opt.patch_rows = int(patch_rows)
         self.smoother = smoother
         self.plan_only = device == "none"
         self._h = L._vp()
@@ -424,11 +421,6 @@ class Solver:
         self._check(self._lib.smg_level_stats(self._h, lv, out))
         keys = ("rows", "nnz_ref", "nnz", "padded", "p_nnz", "p_padded", "pt_padded", "phases")
         return dict(zip(keys, [int(v) for v in out]))
-
-    def dep_stats(self, lv) -> dict:
-        out = (C.c_int64 * 4)()
-        self._check(self._lib.smg_level_dep_stats(self._h, lv, out))
-        return dict(zip(("blocks", "dep_total", "dep_max", "dataflow"), [int(v) for v in out]))
 
     # -- measurement --------------------------------------------------------------------------
     def time_kernel(self, which: str, lv: int = 0, k: int = 1, reps: int = 20, flush_l2: bool = False):
