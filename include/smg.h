@@ -264,6 +264,19 @@ int smg_level_padded_nnz(const smg_handle *h, int lv, int64_t *padded);
  *  [7] smoother phases */
 int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
 
+/* ---- patch smoother (csrc/patch.hpp) -------------------------------
+ * Host-side check of the communication-avoiding schedule of level lv (works on plan-only
+ * handles): lays out one relax call of `iters` sweeps in patches of about target_rows rows
+ * (kind 0: + residual and restriction, 1: prolongation first) and, if verify != 0, proves
+ * symbolically that every row update reads its neighbours at exactly the version the
+ * phase-by-phase schedule would.  out[8]: [0] patches [1] owned rows [2] local rows (owned +
+ * halo, summed over patches) [3] rows whose right-hand side is read [4] row updates
+ * [5] largest patch blob in bytes [6] largest shared-memory vector count [7] bytes of all blobs */
+int smg_patch_plan(const smg_handle *h, int lv, int kind, int iters, int target_rows, int smem_limit,
+                   int verify, int64_t *out);
+/* number of patches level lv is smoothed with on this handle (0: one kernel per colour phase) */
+int smg_level_patched(const smg_handle *h, int lv);
+
 /* ---- measurement ----------------------------------------------------------
  * Times `reps` back-to-back launches of one hot-path kernel on level lv with k
  * right-hand sides using CUDA events on the handle's stream; returns the mean

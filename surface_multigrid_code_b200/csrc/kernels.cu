@@ -14,6 +14,7 @@
 // parity in wavefront mode depends on it.
 #include "kernels.hpp"
 #include "mcf_core.hpp"
+#include "patch.hpp"
 
 #include <algorithm>
 #include <string>
@@ -314,6 +315,42 @@ sell_spmv_ranges_kernel(int trace_slot, RowRanges rr, int nslices, int max_chunk
                                         max_chunk, slice_ptr, col, val, x, ldx, nullptr, y, ldy, nullptr);
 }
 
+// Tail of the residual-norm kernels: per-CTA partial sum (fixed-shape warp / CTA reduction),
+// then the LAST CTA to finish adds all partial sums in a fixed order, so the result does not
+// depend on which CTA that is: deterministic without a second launch.  counter self-resets.
+__device__ __forceinline__ void norm_finish(double d2, double* partial, unsigned int* counter, double* out) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
+  __shared__ double wsum[kBlock / 32];
+  __shared__ bool is_last;
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kBlock) t += ld_vec(partial + i);
+  __shared__ double sm[kBlock];
+  sm[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = kBlock / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *out = sm[0];
+    *counter = 0u;
+  }
+}
+
 // Transfer operators have very short rows (a prolongation row holds at most three
 // entries): one row per thread makes CTAs that move only a few KB each and the kernel
 // becomes bound by CTA turnover.  Here a thread owns R rows (256 apart inside the CTA's
@@ -324,7 +361,7 @@ __global__ void __launch_bounds__(kBlock)
 sell_apply_short_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk,
                         const int* __restrict__ slice_ptr, const int* __restrict__ col,
                         const double* __restrict__ val, const double* x, int ldx, const double* b,
-                        double* y, int ldy, double* z) {
+                        double* y, int ldy, double* z, unsigned int* counter) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
@@ -403,19 +440,7 @@ sell_apply_short_kernel(int trace_slot, int rb, int re, int nslices, int max_chu
       }
     }
   }
-  if (MODE == MODE_NORM) {  // y = per-CTA partial sums; fixed-shape reduction
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
-    __shared__ double wsum[kBlock / 32];
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d2;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
-      y[blockIdx.x] = t;
-    }
-  }
+  if (MODE == MODE_NORM) norm_finish(d2, y, counter, z);  // y = per-CTA partial sums, z = the sum
   trace_end(trace_slot);
 }
 
@@ -423,7 +448,8 @@ template <int K, bool STAGED>
 __global__ void __launch_bounds__(kBlock)
 sell_residual_norm_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk, const int* __restrict__ slice_ptr,
                           const int* __restrict__ col, const double* __restrict__ val,
-                          const double* x, const double* b, int ld, double* __restrict__ partial) {
+                          const double* x, const double* b, int ld, double* partial,
+                          unsigned int* counter, double* out) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
@@ -446,36 +472,7 @@ sell_residual_norm_kernel(int trace_slot, int rb, int re, int nslices, int max_c
       d2 += d * d;
     }
   }
-  // fixed-shape reduction: warp shuffle tree, then the 8 warp sums in order
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
-  __shared__ double wsum[kBlock / 32];
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = d2;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < kBlock / 32; i++) t += wsum[i];
-    partial[blockIdx.x] = t;
-  }
-  trace_end(trace_slot);
-}
-
-__global__ void __launch_bounds__(1024)
-reduce_partials_kernel(int trace_slot, const double* partial, int n, double* __restrict__ out) {
-  trace_begin(trace_slot);
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ double sm[1024];
-  double t = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) t += ld_vec(partial + i);
-  sm[threadIdx.x] = t;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out = sm[0];
+  norm_finish(d2, partial, counter, out);
   trace_end(trace_slot);
 }
 
@@ -787,7 +784,7 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
     const int gs = blocks_for(span, kBlock * R);
     SMG_DISPATCH_K(k, launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<K, MODE, R, W>, gs, kBlock,
                                     static_cast<size_t>(M.max_chunk32) * 12, st, rb, re, M.nslices,
-                                    M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z));
+                                    M.max_chunk32, M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z, nullptr));
     return;
   }
   // large levels, k = 1: two rows per thread (fewer, fatter CTAs; see the Gauss-Seidel kernel)
@@ -796,7 +793,7 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(span, kBlock * 2),
                   kBlock, static_cast<size_t>(M.max_chunk16) * 12, st, rb, re, M.nslices, M.max_chunk16,
-                  M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z);
+                  M.slice_ptr, M.col, v, x, ldx, b, y, ldy, z, nullptr);
     return;
   }
   const int g = blocks_for(span, kBlock);
@@ -854,11 +851,11 @@ void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, i
 int residual_norm_blocks(int nrows) { return blocks_for(nrows > 0 ? nrows + 32 : 1, kBlock); }
 
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
-                           double* scratch, double* out, cudaStream_t st) {
+                           double* scratch, unsigned int* counter, double* out, cudaStream_t st) {
   const int rb = M.row_begin(), re = M.row_end();
   const int span = re > rb ? re - (rb & ~31) : 0;
   if (span <= 0) {  // a rank without rows on this level contributes 0
-    launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, 0, out);
+    launch_fill(out, 0.0, 1, st);
     return;
   }
   int g = blocks_for(span, kBlock);
@@ -868,20 +865,18 @@ void launch_residual_norm2(const SellDev& M, const double* b, const double* x, i
     g = blocks_for(span, kBlock * 2);
     launch_kernel("residual_norm", sell_apply_short_kernel<1, MODE_NORM, 2, kPre>, g, kBlock,
                   static_cast<size_t>(M.max_chunk16) * 12, st, rb, re, M.nslices, M.max_chunk16,
-                  M.slice_ptr, M.col, M.valT, x, ld, b, scratch, ld, nullptr);
-    launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
+                  M.slice_ptr, M.col, M.valT, x, ld, b, scratch, ld, out, counter);
     return;
   }
   if (use_staged(M)) {
     SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, true>, g, kBlock, stage_bytes(M),
                                     st, rb, re, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT,
-                                    x, b, ld, scratch));
+                                    x, b, ld, scratch, counter, out));
   } else {
     SMG_DISPATCH_K(k, launch_kernel("residual_norm", sell_residual_norm_kernel<K, false>, g, kBlock, 0, st, rb,
                                     re, M.nslices, M.max_chunk, M.slice_ptr, M.col, M.valT, x, b, ld,
-                                    scratch));
+                                    scratch, counter, out));
   }
-  launch_kernel("reduce", reduce_partials_kernel, 1, 1024, 0, st, scratch, g, out);
 }
 
 void set_xchg_timeout_ms(long long ms) {
@@ -1397,7 +1392,6 @@ void preload_kernels() {
   preload_one(sell_apply_short_kernel<1, MODE_ADD, 2, kPre>);
   preload_one(sell_apply_short_kernel<1, MODE_SPMV_ZERO, 2, kPre>);
   preload_one(sell_apply_short_kernel<1, MODE_NORM, 2, kPre>);
-  preload_one(reduce_partials_kernel);
   preload_one(halo_exchange_kernel);
   preload_one(fill_kernel);
   preload_one(gather_system_kernel);
@@ -1445,6 +1439,292 @@ void launch_mcf_assemble(int nV, int nF, const int* F, const double* U, const in
 
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
   if (n > 0) launch_kernel("fill", fill_kernel, blocks_for(n, 256), 256, 0, st, p, v, n);
+}
+
+// ---- communication-avoiding patch smoother (patch.hpp) -----------------------------------
+// One CTA per patch.  The patch blob (header, local matrix in ELL form, index lists) is
+// immutable during a solve: ONE cp.async.bulk brings it into shared memory before the PDL
+// wait, i.e. while the previous kernel still runs.  After the wait the CTA gathers u (and b)
+// of its local rows, runs all colour phases of the relax call out of shared memory
+// (__syncthreads between colours instead of kernel boundaries), and writes the rows it owns.
+//   PATCH_DOWN: u_out = relax(u_in); r = b - A u_out on the rows its coarse rows restrict
+//               from; bc = PT r and uc = 0 on those coarse rows    (mg_VCycle.cpp:36-47)
+//   PATCH_UP:   u_out = relax(u_in + P uc)                           (mg_VCycle.cpp:52-56)
+// u_in and u_out are different buffers: other CTAs still read the old values of rows this CTA
+// owns.  Arithmetic per row is that of sell_gs_phase_kernel / sell_apply_* (same entry order,
+// products and sums rounded separately, true division), so results are bit-identical.
+namespace {
+template <int K, int KIND>
+__global__ void __launch_bounds__(kPatchThreads)
+patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long long* __restrict__ off,
+             const double* u_in, double* u_out, const double* b, int ld, const double* uc, double* bc,
+             double* uc_zero, int ldc, const unsigned char* __restrict__ pf_blob,
+             const long long* __restrict__ pf_off, int pf_n) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bar;
+  trace_begin(trace_slot);
+  pdl_launch_dependents();
+  const long long o0 = off[blockIdx.x];
+  const uint32_t bytes = static_cast<uint32_t>(off[blockIdx.x + 1] - o0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, bytes);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dyn)),
+        "l"(blob + o0), "r"(bytes), "r"(smem_u32(&bar))
+        : "memory");
+  }
+  // the blobs of the NEXT patch launch of the V-cycle -> L2 (immutable data, 32 KB pieces)
+  for (int p = blockIdx.x; p < pf_n; p += gridDim.x) {
+    const long long q0 = pf_off[p], q1 = pf_off[p + 1];
+    for (long long q = q0 + 32768ll * (threadIdx.x >> 5); q < q1; q += 32768ll * (blockDim.x >> 5))
+      if ((threadIdx.x & 31) == 0) {
+        const uint32_t nb = static_cast<uint32_t>(q1 - q < 32768 ? q1 - q : 32768);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_blob + q), "r"(nb) : "memory");
+      }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const PatchHeader& H = *reinterpret_cast<const PatchHeader*>(dyn);
+  const int n_loc = H.n_loc, n_b = H.n_b;
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  double* u_loc = reinterpret_cast<double*>(dyn + ((bytes + 15u) & ~15u));
+  double* b_loc = u_loc + static_cast<size_t>(K) * n_loc;
+  double* r_loc = b_loc + static_cast<size_t>(K) * n_b;
+  const int* gid = reinterpret_cast<const int*>(dyn + H.o_gid);
+  pdl_wait();
+  // ---- gather the local rows ----------------------------------------------------------
+  // All global loads of a batch of U rows are issued before the first one is used: a patch
+  // is a few rows per thread, and one dependent round trip per row would dominate the launch.
+  constexpr int U = K == 1 ? 8 : (K == 2 ? 4 : 2);
+  if (KIND == PATCH_UP) {
+    constexpr int WP = 3;  // prolongation rows hold at most three entries (get_prolong.cpp:45-56)
+    const unsigned char* pw = dyn + H.o_pw;
+    const int* pcol = reinterpret_cast<const int*>(dyn + H.o_pcol);
+    const double* pval = reinterpret_cast<const double*>(dyn + H.o_pval);
+    for (int i0 = tid; i0 < n_loc; i0 += nthr * U) {
+      double y[U][K], x[U][WP][K], bv[U][K];
+      int w[U];
+#pragma unroll
+      for (int a = 0; a < U; a++) {
+        const int i = i0 + a * nthr;
+        w[a] = 0;
+        if (i < n_loc) {
+          const int g = gid[i];
+          w[a] = pw[i];
+#pragma unroll
+          for (int q = 0; q < K; q++) y[a][q] = ld_vec(u_in + g + (size_t)q * ld);
+#pragma unroll
+          for (int j = 0; j < WP; j++)
+            if (j < w[a]) {
+              const int c = pcol[(size_t)j * n_loc + i];
+#pragma unroll
+              for (int q = 0; q < K; q++) x[a][j][q] = ld_vec(uc + c + (size_t)q * ldc);
+            }
+          if (i < n_b) {
+#pragma unroll
+            for (int q = 0; q < K; q++) bv[a][q] = ld_vec(b + g + (size_t)q * ld);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < U; a++) {
+        const int i = i0 + a * nthr;
+        if (i >= n_loc) continue;
+        double sum[K];
+#pragma unroll
+        for (int q = 0; q < K; q++) sum[q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < WP; j++)
+          if (j < w[a]) {
+            const double v = pval[(size_t)j * n_loc + i];
+#pragma unroll
+            for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, x[a][j][q]));
+          }
+        for (int j = WP; j < w[a]; j++) {  // wider rows (general P): one at a time
+          const int c = pcol[(size_t)j * n_loc + i];
+          const double v = pval[(size_t)j * n_loc + i];
+#pragma unroll
+          for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, ld_vec(uc + c + (size_t)q * ldc)));
+        }
+#pragma unroll
+        for (int q = 0; q < K; q++) u_loc[i + q * n_loc] = __dadd_rn(y[a][q], sum[q]);
+        if (i < n_b) {
+#pragma unroll
+          for (int q = 0; q < K; q++) b_loc[i + q * n_b] = bv[a][q];
+        }
+      }
+    }
+  } else {
+    for (int i0 = tid; i0 < n_loc; i0 += nthr * U) {
+      double y[U][K], bv[U][K];
+#pragma unroll
+      for (int a = 0; a < U; a++) {
+        const int i = i0 + a * nthr;
+        if (i < n_loc) {
+          const int g = gid[i];
+#pragma unroll
+          for (int q = 0; q < K; q++) y[a][q] = ld_vec(u_in + g + (size_t)q * ld);
+          if (i < n_b) {
+#pragma unroll
+            for (int q = 0; q < K; q++) bv[a][q] = ld_vec(b + g + (size_t)q * ld);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < U; a++) {
+        const int i = i0 + a * nthr;
+        if (i >= n_loc) continue;
+#pragma unroll
+        for (int q = 0; q < K; q++) u_loc[i + q * n_loc] = y[a][q];
+        if (i < n_b) {
+#pragma unroll
+          for (int q = 0; q < K; q++) b_loc[i + q * n_b] = bv[a][q];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- colour phases ------------------------------------------------------------------
+  {
+    const unsigned char* wv = dyn + H.o_w;
+    const unsigned short* col = reinterpret_cast<const unsigned short*>(dyn + H.o_col);
+    const double* val = reinterpret_cast<const double*>(dyn + H.o_val);
+    const double* diag = reinterpret_cast<const double*>(dyn + H.o_diag);
+    const int T = H.T, C = H.C;
+    int g = 0;
+    for (int t = 0; t < T; t++) {
+      const int na = H.n_active[t];
+      const int g0 = H.grp_row[g], gn = H.grp_row[g + 1] - g0, e0 = H.grp_ent[g];
+      for (int r = tid; r < na; r += nthr) {
+        const int row = g0 + r;
+        const int w = wv[row];
+        double sum[K];
+#pragma unroll
+        for (int q = 0; q < K; q++) sum[q] = 0.0;
+        for (int j = 0; j < w; j++) {
+          const int c = col[e0 + j * gn + r];
+          const double v = val[e0 + j * gn + r];
+#pragma unroll
+          for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, u_loc[c + q * n_loc]));
+        }
+        const double d = diag[row];
+#pragma unroll
+        for (int q = 0; q < K; q++) u_loc[row + q * n_loc] = __ddiv_rn(__dsub_rn(b_loc[row + q * n_b], sum[q]), d);
+      }
+      __syncthreads();
+      if (++g == C) g = 0;
+    }
+  }
+  // ---- the rows this patch owns --------------------------------------------------------
+  {
+    const unsigned short* own = reinterpret_cast<const unsigned short*>(dyn + H.o_own);
+    for (int i = tid; i < H.n_own; i += nthr) {
+      const int li = own[i];
+      const int g = gid[li];
+#pragma unroll
+      for (int q = 0; q < K; q++) u_out[g + (size_t)q * ld] = u_loc[li + q * n_loc];
+    }
+  }
+  if (KIND == PATCH_DOWN) {
+    // residual of the rows the owned coarse rows restrict from, then the restriction
+    const int n_R = H.n_R, n_C = H.n_C;
+    const unsigned short* ridx = reinterpret_cast<const unsigned short*>(dyn + H.o_ridx);
+    const unsigned char* rw = dyn + H.o_rw;
+    const unsigned short* rcol = reinterpret_cast<const unsigned short*>(dyn + H.o_rcol);
+    const double* rval = reinterpret_cast<const double*>(dyn + H.o_rval);
+    for (int r = tid; r < n_R; r += nthr) {
+      const int w = rw[r];
+      double sum[K];
+#pragma unroll
+      for (int q = 0; q < K; q++) sum[q] = 0.0;
+      for (int j = 0; j < w; j++) {
+        const int c = rcol[j * n_R + r];
+        const double v = rval[j * n_R + r];
+#pragma unroll
+        for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, u_loc[c + q * n_loc]));
+      }
+      const int li = ridx[r];
+#pragma unroll
+      for (int q = 0; q < K; q++) r_loc[r + q * n_R] = __dsub_rn(b_loc[li + q * n_b], sum[q]);
+    }
+    __syncthreads();
+    const int* cgid = reinterpret_cast<const int*>(dyn + H.o_cgid);
+    const unsigned char* ptw = dyn + H.o_ptw;
+    const unsigned short* ptcol = reinterpret_cast<const unsigned short*>(dyn + H.o_ptcol);
+    const double* ptval = reinterpret_cast<const double*>(dyn + H.o_ptval);
+    for (int r = tid; r < n_C; r += nthr) {
+      const int w = ptw[r];
+      double sum[K];
+#pragma unroll
+      for (int q = 0; q < K; q++) sum[q] = 0.0;
+      for (int j = 0; j < w; j++) {
+        const int c = ptcol[j * n_C + r];
+        const double v = ptval[j * n_C + r];
+#pragma unroll
+        for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, r_loc[c + q * n_R]));
+      }
+      const int I = cgid[r];
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        bc[I + (size_t)q * ldc] = sum[q];
+        uc_zero[I + (size_t)q * ldc] = 0.0;
+      }
+    }
+  }
+  trace_end(trace_slot);
+}
+
+// device-side numeric fill of the matrix values of the patch blobs (numeric precompute)
+__global__ void patch_fill_kernel(double* __restrict__ blob, const int* __restrict__ dst,
+                                  const int* __restrict__ src, const double* __restrict__ csc, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) blob[dst[i]] = csc[src[i]];
+}
+
+template <int K, int KIND>
+void patch_set_attr(size_t smem) {
+  static size_t cur[64] = {0};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > cur[dev]) {
+    cudaFuncSetAttribute(patch_kernel<K, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cur[dev] = smem;
+  }
+}
+}  // namespace
+
+size_t patch_smem_bytes(const PatchDev& P, int k) {
+  return static_cast<size_t>((P.max_blob_bytes + 15) & ~15) + static_cast<size_t>(k) * 8 * P.max_vec_doubles + 16;
+}
+
+void launch_patch_fill(double* blob, const int* dst, const int* src, const double* csc, int64_t n,
+                       cudaStream_t st) {
+  if (n > 0) patch_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(blob, dst, src, csc, n);
+}
+
+void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out, const double* b, int ld,
+                  const double* uc, double* bc, double* uc_zero, int ldc, int k, const PatchDev* next,
+                  cudaStream_t st) {
+  if (P.n_patches <= 0) return;
+  const size_t smem = patch_smem_bytes(P, k);
+  const int threads = P.max_active > 256 ? kPatchThreads : 256;
+  const char* name = kind == PATCH_DOWN ? "patch_down" : "patch_up";
+  const unsigned char* pf_blob = next ? next->blob : nullptr;
+  const long long* pf_off = next ? next->off : nullptr;
+  const int pf_n = next ? next->n_patches : 0;
+  SMG_DISPATCH_K(k, {
+    if (kind == PATCH_DOWN) {
+      patch_set_attr<K, PATCH_DOWN>(smem);
+      launch_kernel(name, patch_kernel<K, PATCH_DOWN>, P.n_patches, threads, smem, st, P.blob, P.off, u_in, u_out, b,
+                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n);
+    } else {
+      patch_set_attr<K, PATCH_UP>(smem);
+      launch_kernel(name, patch_kernel<K, PATCH_UP>, P.n_patches, threads, smem, st, P.blob, P.off, u_in, u_out, b,
+                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n);
+    }
+  });
 }
 
 }  // namespace smg

@@ -74,8 +74,9 @@ void launch_prolong_add(const SellDev& M, const double* x, int ldx, double* u, i
                         cudaStream_t st);
 // *out = || b - M x ||_F^2, deterministic; scratch must hold >= residual_norm_blocks(nrows) doubles
 int residual_norm_blocks(int nrows);
+// counter: one zero-initialised word (the last CTA to finish does the final sum and resets it)
 void launch_residual_norm2(const SellDev& M, const double* b, const double* x, int ld, int k,
-                           double* scratch, double* out, cudaStream_t st);
+                           double* scratch, unsigned int* counter, double* out, cudaStream_t st);
 // Per-launch extras of a Gauss-Seidel phase kernel.
 struct GsFlow {
   // L2 prefetch of the NEXT launch's matrix chunk: CTA b asks for the slices
@@ -177,5 +178,25 @@ void launch_permute_in(const double* in, const int* perm, double* out, int n, in
 void launch_permute_out(const double* in, const int* perm, double* out, int n, int k,
                         cudaStream_t st);
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st);
+
+
+// ---- communication-avoiding patch smoother (patch.hpp, patch.cpp) ------------------------
+constexpr int kPatchThreads = 512;
+struct PatchDev {
+  int n_patches = 0;
+  const unsigned char* blob = nullptr;
+  const long long* off = nullptr;  // n_patches + 1 byte offsets
+  int max_blob_bytes = 0, max_vec_doubles = 0, max_active = 0;
+};
+// dynamic shared memory one CTA needs for k right-hand-side columns
+size_t patch_smem_bytes(const PatchDev& P, int k);
+// kind = PATCH_DOWN: u_out = relax(u_in), bc = PT (b - A u_out), uc_zero = 0
+// kind = PATCH_UP:   u_out = relax(u_in + P uc)
+// next: the patch launch that follows in the V-cycle (its blobs are prefetched into L2), or null
+void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out, const double* b, int ld,
+                  const double* uc, double* bc, double* uc_zero, int ldc, int k, const PatchDev* next,
+                  cudaStream_t st);
+void launch_patch_fill(double* blob, const int* dst, const int* src, const double* csc, int64_t n,
+                       cudaStream_t st);
 
 }  // namespace smg

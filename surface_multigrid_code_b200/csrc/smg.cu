@@ -43,6 +43,7 @@
 
 #include "../../include/smg.h"
 #include "kernels.hpp"
+#include "patch.hpp"
 #include "plan.hpp"
 
 namespace {
@@ -152,6 +153,18 @@ struct LevelDev {
   DevBuf<double> t_val;
   // work vectors (permuted numbering), n x kcap column-major, ld = n
   DevBuf<double> b, u, r;
+  // communication-avoiding patch smoother (patch.hpp): a relax call of this level in one
+  // launch; u2 is the second buffer of u (a patch launch reads one and writes the other)
+  struct PatchBufs {
+    DevBuf<unsigned char> blob;
+    DevBuf<long long> off;
+    DevBuf<int> fill_dst, fill_src;
+    int64_t n_fill = 0;
+    smg::PatchDev view;
+    int iters = -1;
+  } patch_down, patch_up;
+  bool patched = false;
+  DevBuf<double> u2;
   // rows this rank smooths, one range per phase (all rows of the phase unless the level is
   // row-partitioned), and the rows it applies operators to
   std::vector<std::pair<int, int>> gs_ranges;
@@ -264,10 +277,12 @@ struct smg_handle {
   // staging
   DevBuf<double> st_a, st_b, st_c, st_d;
   DevBuf<double> norm_scratch, norm_out;
+  DevBuf<unsigned int> norm_counter;  // zero between launches
   double* h_norm = nullptr;  // pinned
   DevBuf<double> flush;      // L2 flush buffer for smg_time_kernel
 
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+  int patch_kcols = 1;  // right-hand-side columns the patch layouts are sized for
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // mean-curvature-flow assembly (smg_mcf_*)
@@ -434,6 +449,8 @@ int upload_dist(smg_handle* h) {
   return SMG_OK;
 }
 
+int upload_patches(smg_handle* h, int k_cols);
+
 int ensure_k(smg_handle* h, int k) {
   // the pinned residual scratch (h_norm: 1024 doubles, flags from [32], per-rank sums from
   // [64]) is sized for SMG_MAX_RHS columns and 64 ranks
@@ -441,12 +458,30 @@ int ensure_k(smg_handle* h, int k) {
     return fail(h, SMG_E_INVALID, "more than SMG_MAX_RHS right-hand-side columns");
   if (k <= h->kcap) return SMG_OK;
   drop_graphs(h);
+  if (std::min(k, smg::kMaxK) > h->patch_kcols) {
+    // the patch layouts were sized for fewer columns per pass: lay them out again (smaller
+    // patches where needed) and refill their matrix values
+    bool any = false;
+    for (auto& L : h->lv) any = any || L.patched;
+    if (any) {
+      SMG_TRY(upload_patches(h, std::min(k, smg::kMaxK)));
+      for (auto& L : h->lv)
+        if (L.patched)
+          for (LevelDev::PatchBufs* B : {&L.patch_down, &L.patch_up}) {
+            smg::launch_patch_fill(reinterpret_cast<double*>(B->blob.p), B->fill_dst.p, B->fill_src.p, L.a_val.p,
+                                   B->n_fill, h->stream);
+            h->launches++;
+          }
+      SMG_TRY(check_launch(h, "patch refill"));
+    }
+  }
   SMG_CUDA(h, h->coarse_scratch.reserve(smg::dense_sym_scratch_doubles(h->lv.back().n, k)));
   for (auto& L : h->lv) {
     const size_t cnt = static_cast<size_t>(L.n) * k;
     SMG_CUDA(h, L.b.alloc(cnt));
     SMG_CUDA(h, L.u.alloc(cnt));
     SMG_CUDA(h, L.r.alloc(cnt));
+    if (L.patched) SMG_CUDA(h, L.u2.alloc(cnt));
   }
   h->kcap = k;
   return SMG_OK;
@@ -633,6 +668,8 @@ void coarse_solve_device(smg_handle* h, const double* b, double* u, int k) {
   }
 }
 
+bool use_patches(const smg_handle* h, int l, int pre, int post, int k);
+
 // mg_VCycle (src/mg_VCycle.cpp:3-59) unrolled over levels; operates on the resident
 // work vectors lv[l].b / .u of levels l >= lv0.
 void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
@@ -643,6 +680,20 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d down", l);
     smg::trace_label(label);
+    if (use_patches(h, l, pre, post, k)) {  // :36-47 in one launch; u moves to the second buffer
+      for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+        const int kk = std::min(smg::kMaxK, k - k0);
+        const size_t o = static_cast<size_t>(k0) * L.n, oc = static_cast<size_t>(k0) * C.n;
+        // what the V-cycle launches next on a patched level: the down leg of the coarser
+        // level, or (deepest patched level) this level's up leg after the coarse solve
+        const smg::PatchDev* next = l + 1 < last && use_patches(h, l + 1, pre, post, k) ? &C.patch_down.view
+                                                                                         : &L.patch_up.view;
+        smg::launch_patch(L.patch_down.view, smg::PATCH_DOWN, L.u.p + o, L.u2.p + o, L.b.p + o, L.n, nullptr,
+                          C.b.p + oc, C.u.p + oc, C.n, kk, next, h->stream);
+        h->launches++;
+      }
+      continue;
+    }
     relax_device(h, l, pre, L.b.p, L.u.p, k);              // :36
     residual_device(h, l, L.b.p, L.u.p, L.r.p, k);         // :41-42
     if (dist_on(h) && L.layout == smg::LAYOUT_PARTITIONED) exchange(h, L.x_halo_r, L.r.p, L.n, k);
@@ -653,10 +704,22 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
   coarse_solve_device(h, h->lv[last].b.p, h->lv[last].u.p, k);  // :28-33
   for (int l = last - 1; l >= lv0; l--) {
     LevelDev& L = h->lv[l];
+    LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d up", l);
     smg::trace_label(label);
-    prolong_device(h, l, h->lv[l + 1].u.p, L.u.p, k, true);  // :52-53
-    relax_device(h, l, post, L.b.p, L.u.p, k);               // :56
+    if (use_patches(h, l, pre, post, k)) {  // :52-56 in one launch; u returns to the first buffer
+      for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
+        const int kk = std::min(smg::kMaxK, k - k0);
+        const size_t o = static_cast<size_t>(k0) * L.n, oc = static_cast<size_t>(k0) * C.n;
+        const smg::PatchDev* next = l > lv0 && use_patches(h, l - 1, pre, post, k) ? &h->lv[l - 1].patch_up.view : nullptr;
+        smg::launch_patch(L.patch_up.view, smg::PATCH_UP, L.u2.p + o, L.u.p + o, L.b.p + o, L.n, C.u.p + oc, nullptr,
+                          nullptr, C.n, kk, next, h->stream);
+        h->launches++;
+      }
+      continue;
+    }
+    prolong_device(h, l, C.u.p, L.u.p, k, true);  // :52-53
+    relax_device(h, l, post, L.b.p, L.u.p, k);    // :56
   }
 }
 
@@ -708,8 +771,8 @@ int residual_norm_device(smg_handle* h, int l, const double* b, const double* u,
     const size_t o = static_cast<size_t>(k0) * L.n;
     // partitioned: the sum over this rank's rows lands in slot `rank` of the chunk's row
     double* out = part ? D.normv.p + static_cast<size_t>(c) * D.world + D.rank : h->norm_out.p + c;
-    smg::launch_residual_norm2(A, b + o, u + o, L.n, kk, h->norm_scratch.p, out, h->stream);
-    h->launches += 2;
+    smg::launch_residual_norm2(A, b + o, u + o, L.n, kk, h->norm_scratch.p, h->norm_counter.p, out, h->stream);
+    h->launches += 1;
     if (part) exchange(h, D.x_norm, D.normv.p + static_cast<size_t>(c) * D.world, D.world, 1);
   }
   if (part) {
@@ -775,6 +838,12 @@ int numeric_setup(smg_handle* h) {
                           L.sellA.padded, st);
     smg::launch_extract_diag(L.a_val.p, L.diag_pos.p, L.perm.p, L.diag.p, L.n, st);
     h->launches += 2;
+    if (L.patched)
+      for (LevelDev::PatchBufs* B : {&L.patch_down, &L.patch_up}) {
+        smg::launch_patch_fill(reinterpret_cast<double*>(B->blob.p), B->fill_dst.p, B->fill_src.p, L.a_val.p,
+                               B->n_fill, st);
+        h->launches++;
+      }
   }
   SMG_TRY(check_launch(h, "numeric setup"));
   // coarse factorisation (cpp:46-48, :253-254): dense Cholesky, explicit inverse
@@ -824,6 +893,74 @@ int numeric_setup(smg_handle* h) {
   return SMG_OK;
 }
 
+// Patch smoother: levels small enough to be latency-bound (multicolour mode).  A level is
+// patched when both of its launches (down: pre-smoothing + residual + restriction; up:
+// prolongation + post-smoothing) can be laid out; otherwise it keeps one kernel per phase.
+int upload_patches(smg_handle* h, int k_cols) {
+  smg::Plan& pl = h->plan;
+  h->patch_kcols = k_cols;
+  for (auto& L : h->lv) L.patched = false;
+  const int nlev = static_cast<int>(pl.lv.size());
+  cudaStream_t st = h->stream;
+  if (h->opt.smoother != SMG_SMOOTHER_MULTICOLOUR || h->opt.patch_rows < 0) return SMG_OK;
+  int max_rows = 70000;
+  if (const char* e = std::getenv("SMG_PATCH_MAX_ROWS")) max_rows = std::atoi(e);
+  int dev_smem = 0, nsm = 0;
+  cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  if (dev_smem <= 0 || nsm <= 0) return SMG_OK;
+  const int budget = dev_smem - 1024;  // static shared memory of the kernel + alignment slack
+  for (int l = 0; l + 1 < nlev; l++) {
+    const smg::LevelPlan& P = pl.lv[l];
+    LevelDev& L = h->lv[l];
+    if (P.n <= 0 || P.n > max_rows || P.layout == smg::LAYOUT_PARTITIONED) continue;
+    // one patch per SM unless that makes patches too small to amortise their halo
+    int target = h->opt.patch_rows > 0 ? h->opt.patch_rows : std::max(96, (P.n + nsm - 1) / nsm);
+    smg::PatchSet down, up;
+    std::string why;
+    if (!smg::build_patches(pl, l, smg::PATCH_DOWN, h->opt.pre_relax, target, budget, k_cols, &down, &why) ||
+        !smg::build_patches(pl, l, smg::PATCH_UP, h->opt.post_relax, target, budget, k_cols, &up, &why))
+      continue;
+    if (std::getenv("SMG_PATCH_VERIFY")) {
+      for (const smg::PatchSet* ps : {&down, &up}) {
+        const std::string err = smg::verify_patches(pl, *ps);
+        if (!err.empty()) return fail(h, SMG_E_INTERNAL, "patch plan of level " + std::to_string(l) + ": " + err);
+      }
+    }
+    auto put = [&](const smg::PatchSet& ps, LevelDev::PatchBufs& B) -> int {
+      SMG_CUDA(h, B.blob.upload(ps.blob, st));
+      SMG_CUDA(h, B.off.upload(ps.off, st));
+      SMG_CUDA(h, B.fill_dst.upload(ps.fill_dst, st));
+      SMG_CUDA(h, B.fill_src.upload(ps.fill_src, st));
+      B.n_fill = static_cast<int64_t>(ps.fill_dst.size());
+      B.iters = ps.iters;
+      B.view.n_patches = ps.n_patches;
+      B.view.blob = B.blob.p;
+      B.view.off = B.off.p;
+      B.view.max_blob_bytes = ps.max_blob_bytes;
+      B.view.max_vec_doubles = ps.max_vec_doubles;
+      B.view.max_active = ps.max_active;
+      return SMG_OK;
+    };
+    SMG_TRY(put(down, L.patch_down));
+    SMG_TRY(put(up, L.patch_up));
+    SMG_CUDA(h, cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    L.patched = true;
+  }
+  return SMG_OK;
+}
+
+// level l runs its relax calls as patch launches for this V-cycle shape
+bool use_patches(const smg_handle* h, int l, int pre, int post, int k) {
+  const LevelDev& L = h->lv[l];
+  if (!L.patched || pre != L.patch_down.iters || post != L.patch_up.iters) return false;
+  const int kk = std::min(k, smg::kMaxK);
+  int dev_smem = 0;
+  cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  return static_cast<int>(smg::patch_smem_bytes(L.patch_down.view, kk)) + 64 <= dev_smem &&
+         static_cast<int>(smg::patch_smem_bytes(L.patch_up.view, kk)) + 64 <= dev_smem;
+}
+
 int upload_plan(smg_handle* h) {
   smg::Plan& pl = h->plan;
   const int nlev = static_cast<int>(pl.lv.size());
@@ -868,6 +1005,7 @@ int upload_plan(smg_handle* h) {
       h->launches += 2;
     }
   }
+  SMG_TRY(upload_patches(h, 1));
   SMG_CUDA(h, h->lhs_src.upload(pl.lhs_src, st));
   // permuted unknown row -> caller index
   const std::vector<int>& perm0 = pl.lv[0].order.perm;
@@ -1189,6 +1327,11 @@ int smg_create(smg_handle** out, const smg_options* opt) {
     smg_destroy(h);
     return SMG_E_CUSOLVER;
   }
+  if (h->norm_counter.alloc(4) != cudaSuccess ||
+      cudaMemsetAsync(h->norm_counter.p, 0, 4 * sizeof(unsigned int), h->stream) != cudaSuccess) {
+    smg_destroy(h);
+    return SMG_E_CUDA;
+  }
   *out = h;
   return SMG_OK;
 }
@@ -1210,7 +1353,7 @@ void smg_destroy(smg_handle* h) {
     h->auk_csc_val.release(); h->auk_val.release(); h->kidx.release(); h->ksrc.release();
     h->ainv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
-    h->norm_scratch.release(); h->norm_out.release(); h->flush.release();
+    h->norm_scratch.release(); h->norm_out.release(); h->norm_counter.release(); h->flush.release();
     h->mcf.F.release(); h->mcf.vf_ptr.release(); h->mcf.vf_face.release(); h->mcf.Lval.release();
     h->mcf.dblA.release(); h->mcf.mass.release(); h->mcf.U.release(); h->mcf.rhs.release(); h->mcf.z.release();
     DistCtx& D = h->dist;
@@ -1996,6 +2139,34 @@ int smg_level_stats(const smg_handle* h, int lv, int64_t* out) {
   return SMG_OK;
 }
 
+int smg_patch_plan(const smg_handle* h, int lv, int kind, int iters, int target_rows, int smem_limit,
+                   int verify, int64_t* out) {
+  SMG_TRY(check_ready(h, false));
+  if (!out || (kind != smg::PATCH_DOWN && kind != smg::PATCH_UP)) return SMG_E_INVALID;
+  smg::PatchSet ps;
+  std::string why;
+  if (!smg::build_patches(h->plan, lv, kind, iters, target_rows, smem_limit > 0 ? smem_limit : 226 * 1024, 1, &ps, &why))
+    return fail(const_cast<smg_handle*>(h), SMG_E_UNSUPPORTED, "patch plan: " + why);
+  if (verify) {
+    const std::string err = smg::verify_patches(h->plan, ps);
+    if (!err.empty()) return fail(const_cast<smg_handle*>(h), SMG_E_INTERNAL, "patch plan: " + err);
+  }
+  out[0] = ps.n_patches;
+  out[1] = ps.sum_own;
+  out[2] = ps.sum_loc;
+  out[3] = ps.sum_b;
+  out[4] = ps.sum_updates;
+  out[5] = ps.max_blob_bytes;
+  out[6] = ps.max_vec_doubles;
+  out[7] = static_cast<int64_t>(ps.blob.size());
+  return SMG_OK;
+}
+
+int smg_level_patched(const smg_handle* h, int lv) {
+  if (!h || h->plan_only || lv < 0 || lv >= static_cast<int>(h->lv.size())) return 0;
+  return h->lv[lv].patched ? h->lv[lv].patch_down.view.n_patches : 0;
+}
+
 // ---- measurement -----------------------------------------------------------------
 int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush_l2,
                     float* ms_per_rep, int* launches_per_rep) {
@@ -2033,8 +2204,8 @@ int smg_time_kernel(smg_handle* h, int which, int lv, int k, int reps, int flush
           break;
         }
         smg::launch_residual_norm2(own_rows(h, L, L.sellA.view()), L.b.p, L.u.p, L.n,
-                                   std::min(k, smg::kMaxK), h->norm_scratch.p, h->norm_out.p, h->stream);
-        h->launches += 2;
+                                   std::min(k, smg::kMaxK), h->norm_scratch.p, h->norm_counter.p, h->norm_out.p, h->stream);
+        h->launches += 1;
         break;
       }
       case SMG_K_COARSE_SOLVE: coarse_solve_device(h, L.b.p, L.u.p, k); break;
@@ -2096,7 +2267,7 @@ int smg_trace_iteration(smg_handle* h, int k, int max_events, char* names, int n
   if (e == cudaSuccess) {
     const bool part = dist_on(h) && L0.layout == smg::LAYOUT_PARTITIONED;
     smg::launch_residual_norm2(own_rows(h, L0, L0.sellA.view()), L0.b.p, L0.u.p, L0.n,
-                               std::min(k, smg::kMaxK), h->norm_scratch.p,
+                               std::min(k, smg::kMaxK), h->norm_scratch.p, h->norm_counter.p,
                                part ? h->dist.normv.p + h->dist.rank : h->norm_out.p, h->stream);
     if (part) exchange(h, h->dist.x_norm, h->dist.normv.p, h->dist.world, 1);
     vcycle_device(h, 0, h->opt.pre_relax, h->opt.post_relax, k);

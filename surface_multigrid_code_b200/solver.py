@@ -422,6 +422,18 @@ class Solver:
         keys = ("rows", "nnz_ref", "nnz", "padded", "p_nnz", "p_padded", "pt_padded", "phases")
         return dict(zip(keys, [int(v) for v in out]))
 
+    def patch_plan(self, lv: int, kind: str = "down", iters: int = 2, target_rows: int = 256,
+                   smem_limit: int = 0, verify: bool = True) -> dict:
+        """Lay out (and verify symbolically) the patch schedule of level lv; host only."""
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.smg_patch_plan(self._h, lv, {"down": 0, "up": 1}[kind], iters, target_rows,
+                                             smem_limit, int(verify), out))
+        keys = ("patches", "owned", "local", "rhs_rows", "updates", "max_blob_bytes", "max_vec", "blob_bytes")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def level_patched(self, lv: int) -> int:
+        return int(self._lib.smg_level_patched(self._h, lv))
+
     # -- measurement --------------------------------------------------------------------------
     def time_kernel(self, which: str, lv: int = 0, k: int = 1, reps: int = 20, flush_l2: bool = False):
         """-> (mean ms per rep, kernel launches per rep); CUDA events on the handle's stream."""
