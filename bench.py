@@ -39,24 +39,52 @@ sys.path.insert(0, ROOT)
 METRIC = "V-cycles/sec (1M-vertex sphere Poisson, 5-level V(2,2), FP64)"  # the default workload
 
 
-def metric_name(pr):
-    if pr.n == 1048578 and pr.nlev == 5:
+def metric_name(pr, args=None):
+    if pr.n == 1048578 and pr.nlev == 5 and (args is None or args.workload == "sphere"):
         return METRIC
-    return f"V-cycles/sec ({pr.n}-vertex sphere Poisson, {pr.nlev}-level V(2,2), FP64)"
+    wl = args.workload if args is not None else "sphere"
+    return f"V-cycles/sec ({pr.n}-vertex {wl} Poisson, {pr.nlev}-level V(2,2), FP64)"
 
 UNIT = "V-cycles/s"
 FALLBACK_HBM_GBS = 6650.0
 
 
-def build_problem(n_sub: int, n_levels: int, max_iter: int = 20):
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_problem(args):
+    """The Poisson workloads.  sphere: BASELINE configs[2] (default) and its 4M-vertex sibling;
+    hilbert: configs[4], hilbert_cube.obj upsampled --subdiv times (3 = 4 028 672 vertices), 346
+    nearest-vertex constraints, 3 subdivision levels + the original mesh + 2 stand-in coarsened
+    levels (tests/golden/make_hilbert.py); bunny / ogre: configs[0-1], the reference's meshes with
+    03_mg_solver's settings and the stand-in hierarchy of tests/golden/make_golden.py."""
     from surface_multigrid_code_b200 import meshgen as mg
 
-    return mg.sphere_problem(n_sub, n_levels, tol=1e-10, max_iter=max_iter, pad_three=True)
+    wl = args.workload
+    if wl == "sphere":
+        return mg.sphere_problem(args.subdiv, args.levels, tol=1e-10, max_iter=args.max_iter, pad_three=True)
+    if wl == "hilbert":
+        d = np.load(os.path.join(GOLDEN, "hilbert_cube_base.npz"))
+        Pc = [mg.load_csc_keep_zeros(d, "Pc0"), mg.load_csc_keep_zeros(d, "Pc1")]
+        return mg.upsampled_mesh_problem("hilbert_cube", d["V"], d["F"], d["known"], Pc, args.subdiv, tol=1e-10,
+                                         max_iter=args.max_iter)
+    if wl in ("bunny", "ogre"):
+        name = {"bunny": "bunny_l3", "ogre": "ogre_l4"}[wl]
+        d = np.load(os.path.join(GOLDEN, name + ".npz"))
+        n, nlev = int(d["n"]), int(d["nlev"])
+        import scipy.sparse as sp
+
+        A = sp.csc_matrix((d["A_data"], d["A_indices"], d["A_indptr"]), shape=(n, n))
+        P = [mg.load_csc_keep_zeros(d, f"P{l}") for l in range(nlev - 1)]
+        return mg.Problem(wl, A, P, d["known"], d["known_val"], d["rhs"], d["z0"], args.tol or float(d["tol"]),
+                          args.max_iter)
+    raise SystemExit(f"bench.py: unknown workload {wl}")
 
 
 def workload_config(pr, args, extra=None):
     cfg = {
-        "workload": f"sphere_subdiv{args.subdiv}_{pr.n}v_{pr.nlev}level_poisson_fp64",
+        "workload": (f"sphere_subdiv{args.subdiv}_{pr.n}v_{pr.nlev}level_poisson_fp64" if args.workload == "sphere"
+                     else f"{args.workload}_{pr.n}v_{pr.nlev}level_poisson_fp64"),
         "vertices": int(pr.n),
         "nnz_A": int(pr.A.nnz),
         "levels": int(pr.nlev),
@@ -111,7 +139,10 @@ def iteration_bytes(stats, k=1):
         tot += 4 * bytes_gs_sweep(n, nnz, k) + bytes_residual(n, nnz, k)
         tot += bytes_restrict(n, nc, pnnz, k) + bytes_prolong_add(n, nc, pnnz, k)
     nc = stats[-1]["rows"]
-    tot += 8 * nc * nc + 24 * nc * k  # dense inverse apply
+    # coarse direct solve: the kernel reads the packed lower-triangular 64x64 tiles of the dense
+    # symmetric inverse (half the matrix), b, and reads + writes u
+    nblk = (nc + 63) // 64
+    tot += 8 * 64 * 64 * (nblk * (nblk + 1) // 2) + 24 * nc * k
     return tot
 
 
@@ -248,14 +279,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pr = build_problem(args.subdiv, args.levels, args.max_iter)
+    pr = build_problem(args)
     impl, kind, what = cpu_impl()
     times = cpu_iterations(pr, args.warmup, args.steps, impl)
     total = sum(times)
     v = args.steps / total
     line = {
         "impl": "reference",
-        "metric": metric_name(pr), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric_name(pr, args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(pr, args, {"parallelism": "host cpu, 1 thread"}),
@@ -291,7 +322,7 @@ def run_gpu(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    pr = build_problem(args.subdiv, args.levels, args.max_iter)
+    pr = build_problem(args)
     s = Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph)
     # N > 1: ONE problem, its fine levels partitioned by rows over the N GPUs (halo exchange
     # through peer-mapped memory inside the V-cycle graph); --replicas: N independent problems
@@ -420,26 +451,34 @@ def run_gpu(args):
     except Exception as e:  # profiling aid only
         in_situ = {"error": str(e)}
     clk = clocks.stop()
-    traffic, traffic_note = None, None
+    traffic, traffic_pair, traffic_note = None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
         traffic, traffic_note = tj.get("relax_sweep_dram_bytes"), tj.get("note")
+        traffic_pair = tj.get("relax_pair_dram_bytes_per_sweep")
     except Exception:
         pass
     gs = kern["relax_sweep"]
     pre_sweeps = max(nl_pre // max(gs["launches"], 1), 1)
     pre_gbs = pre_sweeps * gs["algorithmic_bytes"] / (ms_pre * 1e-3) / 1e9
+    # `frac` is the HBM-honest figure: ONE sweep with L2 flushed before it (its DRAM traffic equals
+    # its algorithmic bytes, profiles/).  The pair of pre-smoothing sweeps as a V-cycle runs them
+    # and the in-situ device timeline are L2-assisted (the second sweep finds part of the 88 MB
+    # matrix in the 126 MB L2) and are reported beside it, not as the roofline fraction.
     roofline = {
-        "bound": "hbm", "kernel": "sell_gs_phase_kernel (fine-level Gauss-Seidel, "
-                                  f"{gs['launches']} colour launches per sweep)",
-        "achieved": pre_gbs, "peak": peak, "unit": "GB/s", "frac": pre_gbs / peak, "traffic": traffic,
+        "bound": "hbm", "kernel": "fine-level Gauss-Seidel sweep "
+                                  f"({gs['launches']} colour launches of sell_gs_phase_multi_kernel per sweep)",
+        "achieved": gs["gbs"], "peak": peak, "unit": "GB/s", "frac": gs["frac"], "traffic": traffic,
         "traffic_note": traffic_note,
         "peak_source": peak_src, "algorithmic_bytes_per_sweep": gs["algorithmic_bytes"],
-        "ms_per_sweep": ms_pre / pre_sweeps,
-        "how": f"{pre_sweeps} pre-smoothing sweeps back to back as inside a V-cycle, CUDA events on the "
-               "library stream, L2 flushed before each pair; single cold sweep and the in-situ device "
-               "timeline are in kernels.relax_sweep / in_situ",
+        "ms_per_sweep": gs["ms"],
+        "how": "one sweep (all colour launches), L2 flushed before every sweep (256 MB write), CUDA events on the "
+               "library stream, mean of 20; algorithmic bytes = 12 nnz + 4 (n + 1) + 8 n + 24 n k (SURVEY.md 8d)",
+        "warm_pair": {"achieved": pre_gbs, "frac": pre_gbs / peak, "ms_per_sweep": ms_pre / pre_sweeps,
+                      "traffic_per_sweep": traffic_pair,
+                      "how": f"{pre_sweeps} pre-smoothing sweeps back to back as inside a V-cycle, L2 flushed before "
+                             "each pair only: L2-assisted, NOT an HBM roofline fraction"},
         "in_situ": in_situ,
         "iteration": {"algorithmic_bytes": iteration_bytes(stats, k), "ms": ms_iter,
                       "gbs": iteration_bytes(stats, k) / (ms_iter * 1e-3) / 1e9,
@@ -480,7 +519,7 @@ def run_gpu(args):
     barrier()
     if rank == 0:
         line = {
-            "metric": metric_name(pr), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(pr, args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None,
             "dtype": "f64",
@@ -514,16 +553,179 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------
+# BASELINE configs[3]: mean-curvature flow (05_example_mean_curvature_flow/main.cpp:57-79)
+# --------------------------------------------------------------------------------------
+def build_mcf(args):
+    """The 1M-vertex sphere with a seeded radial perturbation (something to flow), its
+    subdivision hierarchy, the cotangent matrix of the rest shape (main.cpp:41, computed once)."""
+    from surface_multigrid_code_b200 import meshgen as mg
+
+    V0, F0 = mg.octahedron()
+    V, F, P = mg.subdivision_hierarchy(V0, F0, args.subdiv, args.levels, project_sphere=True, pad_three=True)
+    rng = np.random.default_rng(0)
+    V = V * (1.0 + 0.02 * rng.standard_normal((V.shape[0], 1)))
+    V = mg.normalize_unit_area(V, F)
+    L0 = mg.cotmatrix(V, F).tocsc()
+    L0.sort_indices()
+    return V, np.ascontiguousarray(F, dtype=np.int32), P, L0
+
+
+def run_mcf(args):
+    """One line for configs[3].  A step = one flow step: M = massmatrix(U), LHS = M - 0.01 L,
+    RHS = M U, min_quad_with_fixed_mg_precompute(LHS), min_quad_with_fixed_mg_solve(RHS, U, 5e-7),
+    normalize_unit_area.  GPU arm: smg_mcf_step (assembly, Galerkin refresh and coarse
+    factorisation on the device; only U crosses the bus); value = V-cycles/s over the solves,
+    per-step precompute and solve times beside it.  --impl reference: the same steps through the
+    reference's own sources on one host thread (assembly in numpy, not timed)."""
+    from surface_multigrid_code_b200 import meshgen as mg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    delta, tol, max_iter = 0.01, 5e-7, 20
+    V, F, P, L0 = build_mcf(args)
+    n = V.shape[0]
+    cfg = {"workload": f"mcf_sphere_subdiv{args.subdiv}_{n}v_{args.levels}level_k3_fp64", "vertices": int(n),
+           "nnz_A": int(L0.nnz), "levels": args.levels, "rhs_columns": 3, "pre_post": [2, 2], "tol": tol,
+           "delta": delta, "flow_steps": args.flow_steps,
+           "data_layout": "reference P layout (3 stored entries per row, explicit zeros)"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle.cpu_oracle import Oracle
+
+        impl, kind, what = cpu_impl()
+        U = np.asfortranarray(V.copy())
+        steps = max(1, min(args.flow_steps, args.steps if args.steps < 10 else 2))
+        t_pre = t_solve = 0.0
+        cycles = 0
+        ora = Oracle(P, impl=impl)
+        for _ in range(steps):
+            pr = mg.mcf_step_problem(V, F, P, U=U, delta=delta, tol=tol, max_iter=max_iter, L0=L0)
+            t0 = time.perf_counter()
+            ora.precompute(pr.A, None)
+            t1 = time.perf_counter()
+            z, r_his, ok = ora.solve(pr.rhs, pr.z0, None, tol, max_iter)
+            t2 = time.perf_counter()
+            t_pre += t1 - t0
+            t_solve += t2 - t1
+            cycles += len(r_his) - 1
+            U = np.asfortranarray(mg.normalize_unit_area(z, F))
+        v = cycles / t_solve
+        line = {"impl": "reference", "metric": f"V-cycles/sec (mean-curvature flow, {n} vertices, k = 3, FP64)",
+                "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+                "ms_per_step": 1e3 * (t_pre + t_solve) / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(cfg, parallelism="host cpu, 1 thread"),
+                "mcf": {"flow_steps_timed": steps, "precompute_ms_per_step": 1e3 * t_pre / steps,
+                        "solve_ms_per_step": 1e3 * t_solve / steps, "vcycles_per_step": cycles / steps},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                 "sample": f"{steps} flow steps (precompute + solve to {tol}); {what}"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+
+    from surface_multigrid_code_b200.solver import Solver
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    s = Solver(smoother=args.smoother, device=local_rank, use_graph=not args.no_graph)
+    if world > 1:
+        s.dist_init(rank, world, (args.comm_mb or max(256, (n * 4 * 16 * 2 * 5 // 4 >> 20) + 16)) << 20)
+        s.dist_options(args.halo, args.dist_levels, args.dist_min_rows)
+        s.dist_connect_torch()
+    pr0 = mg.mcf_step_problem(V, F, P, U=V, delta=delta, tol=tol, max_iter=max_iter, L0=L0)
+    t0 = time.perf_counter()
+    s.set_hierarchy(P).precompute(pr0.A, None)
+    s.mcf_setup(F, L0, delta)
+    t_setup = time.perf_counter() - t0
+
+    def flow(nsteps, U):
+        pre = sol = copy = 0.0
+        cyc = 0
+        wall0 = time.perf_counter()
+        for _ in range(nsteps):
+            z, r_his, ok = s.mcf_step(U, tol, max_iter)
+            tm = s.timings()
+            pre += tm["precompute_device_ms"]
+            sol += tm["solve_ms"]
+            copy += tm["d2h_ms"]
+            cyc += len(r_his) - 1
+            U = np.asfortranarray(mg.normalize_unit_area(z, F))
+        return U, pre, sol, copy, cyc, time.perf_counter() - wall0
+
+    U = np.asfortranarray(V.copy())
+    flow(max(1, min(args.warmup, 2)), U)  # graph capture, allocations
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(1.5)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = s.launch_count
+    U, pre, sol, copy, cyc, wall = flow(args.flow_steps, U)
+    launches = s.launch_count - l0
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    t = torch.tensor([pre, sol, copy, wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pre, sol, copy, wall = (float(x) for x in t)
+    assert np.all(np.isfinite(U))
+    if rank == 0:
+        nst = args.flow_steps
+        line = {"metric": f"V-cycles/sec (mean-curvature flow, {n} vertices, k = 3, FP64)",
+                "value": cyc / (sol * 1e-3), "unit": UNIT, "n_gpus": world, "steps": nst,
+                "warmup": max(1, min(args.warmup, 2)), "ms_per_step": (pre + sol + copy) / nst,
+                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": dict(cfg, parallelism="single GPU" if world == 1 else
+                               f"fine levels row-partitioned over {world} GPUs", smoother=args.smoother,
+                               setup_s=t_setup),
+                "mcf": {"flow_steps_timed": nst, "precompute_ms_per_step": pre / nst, "solve_ms_per_step": sol / nst,
+                        "d2h_ms_per_step": copy / nst, "vcycles_per_step": cyc / nst,
+                        "wall_ms_per_step_incl_host_normalisation": 1e3 * wall / nst,
+                        "what": "precompute = device-side assembly of M - delta L and M U, Galerkin products of all "
+                                "levels, diagonals, dense coarse factorisation (smg_mcf_step, H2D of U included); "
+                                "solve = the solve loop on the device (k = 3)"},
+                "e2e": {"value": cyc / (1e-3 * (pre + sol + copy)), "unit": UNIT,
+                        "h2d_bytes_per_step": 24 * n * world, "d2h_bytes_per_step": 24 * n * world,
+                        "step": "one smg_mcf_step call with host U in / out (assembly + precompute + solve)"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--subdiv", type=int, default=9, help="octahedron subdivisions (9 = 1M vertices)")
+    ap.add_argument("--workload", default="sphere", choices=["sphere", "hilbert", "bunny", "ogre", "mcf"],
+                    help="sphere: BASELINE configs[2] (default); hilbert: configs[4]; bunny / ogre: configs[0-1]; "
+                         "mcf: configs[3] (10 mean-curvature-flow steps, k = 3)")
+    ap.add_argument("--subdiv", type=int, default=None,
+                    help="sphere / mcf: octahedron subdivisions (default 9 = 1M vertices); hilbert: upsampling "
+                         "steps (default 3 = 4M vertices)")
     ap.add_argument("--levels", type=int, default=5)
-    ap.add_argument("--max-iter", type=int, default=20,
-                    help="maxIter of the solve (reference default 20; the 4M sphere needs ~24 cycles for 1e-10)")
+    ap.add_argument("--max-iter", type=int, default=None,
+                    help="maxIter of the solve (reference default 20; the 4M meshes need more for 1e-10: default 40)")
+    ap.add_argument("--tol", type=float, default=None, help="bunny / ogre: tolerance (default: the fixture's 1e-3)")
+    ap.add_argument("--flow-steps", type=int, default=10, help="mcf: flow steps (05_example: one per key press)")
     ap.add_argument("--smoother", default="multicolour", choices=["multicolour", "wavefront"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -537,7 +739,13 @@ def main():
     ap.add_argument("--dist-min-rows", type=int, default=0)
     ap.add_argument("--comm-mb", type=int, default=0, help="peer-mapped staging buffer per GPU (0 = auto)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.subdiv is None:
+        args.subdiv = 3 if args.workload == "hilbert" else 9
+    if args.max_iter is None:
+        args.max_iter = 40 if args.workload == "hilbert" else 20
+    if args.workload == "mcf":
+        run_mcf(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -94,14 +94,20 @@ struct TraceState {
 };
 thread_local TraceState g_trace;
 
+int g_trace_sub = 0;  // extra trace slots of the next launch (stages inside the kernel)
+const char* const* g_trace_sub_names = nullptr;
+
 template <class... KArgs, class... Args>
 void launch_kernel(const char* name, void (*kernel)(int, KArgs...), int grid, int block, size_t smem,
                    cudaStream_t st, Args... args) {
   int slot = -1;
-  if (g_trace.on && g_trace.next < g_trace.cap) {
+  if (g_trace.on && g_trace.next + g_trace_sub < g_trace.cap) {
     slot = g_trace.next++;
     g_trace.names.push_back(g_trace.label + " " + name + " g" + std::to_string(grid));
+    for (int i = 0; i < g_trace_sub; i++, g_trace.next++)
+      g_trace.names.push_back(g_trace.label + " " + name + g_trace_sub_names[i]);
   }
+  g_trace_sub = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -1454,6 +1460,40 @@ void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
 // owns.  Arithmetic per row is that of sell_gs_phase_kernel / sell_apply_* (same entry order,
 // products and sums rounded separately, true division), so results are bit-identical.
 namespace {
+// sum[q] += sum_j val[j * stride + r] * x[col[j * stride + r] + q * ldx] over the first w entries of
+// ELL row r, in entry order, products and sums rounded separately.  The first WMAX entries are
+// fetched together (indices, then values and gathers) before the dependent chain of additions.
+template <int K, int WMAX, class ColT>
+__device__ __forceinline__ void ell_row_sum(const ColT* __restrict__ col, const double* __restrict__ val, int stride,
+                                            int r, int w, const double* x, int ldx, double (&sum)[K]) {
+  int c[WMAX];
+  double v[WMAX], xv[WMAX][K];
+#pragma unroll
+  for (int j = 0; j < WMAX; j++)
+    if (j < w) {
+      c[j] = col[j * stride + r];
+      v[j] = val[j * stride + r];
+    }
+#pragma unroll
+  for (int j = 0; j < WMAX; j++)
+    if (j < w) {
+#pragma unroll
+      for (int q = 0; q < K; q++) xv[j][q] = x[c[j] + q * ldx];
+    }
+#pragma unroll
+  for (int j = 0; j < WMAX; j++)
+    if (j < w) {
+#pragma unroll
+      for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v[j], xv[j][q]));
+    }
+  for (int j = WMAX; j < w; j++) {
+    const int cc = col[j * stride + r];
+    const double vv = val[j * stride + r];
+#pragma unroll
+    for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(vv, x[cc + q * ldx]));
+  }
+}
+
 template <int K, int KIND>
 __global__ void __launch_bounds__(kPatchThreads)
 patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long long* __restrict__ off,
@@ -1463,6 +1503,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
+  trace_begin(trace_slot < 0 ? -1 : trace_slot + 1);
   pdl_launch_dependents();
   const long long o0 = off[blockIdx.x];
   const uint32_t bytes = static_cast<uint32_t>(off[blockIdx.x + 1] - o0);
@@ -1485,6 +1526,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
   }
   __syncthreads();
   mbar_wait(&bar, 0);
+  trace_end(trace_slot < 0 ? -1 : trace_slot + 1);  // sub-slots (tracing only): blob in shared memory
   const PatchHeader& H = *reinterpret_cast<const PatchHeader*>(dyn);
   const int n_loc = H.n_loc, n_b = H.n_b;
   const int nthr = blockDim.x, tid = threadIdx.x;
@@ -1493,6 +1535,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
   double* r_loc = b_loc + static_cast<size_t>(K) * n_b;
   const int* gid = reinterpret_cast<const int*>(dyn + H.o_gid);
   pdl_wait();
+  trace_begin(trace_slot < 0 ? -1 : trace_slot + 2);  // gather
   // ---- gather the local rows ----------------------------------------------------------
   // All global loads of a batch of U rows are issued before the first one is used: a patch
   // is a few rows per thread, and one dependent round trip per row would dominate the launch.
@@ -1585,6 +1628,8 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
     }
   }
   __syncthreads();
+  trace_end(trace_slot < 0 ? -1 : trace_slot + 2);
+  trace_begin(trace_slot < 0 ? -1 : trace_slot + 3);  // colour phases
   // ---- colour phases ------------------------------------------------------------------
   {
     const unsigned char* wv = dyn + H.o_w;
@@ -1602,12 +1647,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
         double sum[K];
 #pragma unroll
         for (int q = 0; q < K; q++) sum[q] = 0.0;
-        for (int j = 0; j < w; j++) {
-          const int c = col[e0 + j * gn + r];
-          const double v = val[e0 + j * gn + r];
-#pragma unroll
-          for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, u_loc[c + q * n_loc]));
-        }
+        ell_row_sum<K, 8>(col + e0, val + e0, gn, r, w, u_loc, n_loc, sum);
         const double d = diag[row];
 #pragma unroll
         for (int q = 0; q < K; q++) u_loc[row + q * n_loc] = __ddiv_rn(__dsub_rn(b_loc[row + q * n_b], sum[q]), d);
@@ -1616,6 +1656,8 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
       if (++g == C) g = 0;
     }
   }
+  trace_end(trace_slot < 0 ? -1 : trace_slot + 3);
+  trace_begin(trace_slot < 0 ? -1 : trace_slot + 4);  // write-back, residual, restriction
   // ---- the rows this patch owns --------------------------------------------------------
   {
     const unsigned short* own = reinterpret_cast<const unsigned short*>(dyn + H.o_own);
@@ -1638,12 +1680,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
       double sum[K];
 #pragma unroll
       for (int q = 0; q < K; q++) sum[q] = 0.0;
-      for (int j = 0; j < w; j++) {
-        const int c = rcol[j * n_R + r];
-        const double v = rval[j * n_R + r];
-#pragma unroll
-        for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, u_loc[c + q * n_loc]));
-      }
+      ell_row_sum<K, 8>(rcol, rval, n_R, r, w, u_loc, n_loc, sum);
       const int li = ridx[r];
 #pragma unroll
       for (int q = 0; q < K; q++) r_loc[r + q * n_R] = __dsub_rn(b_loc[li + q * n_b], sum[q]);
@@ -1658,12 +1695,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
       double sum[K];
 #pragma unroll
       for (int q = 0; q < K; q++) sum[q] = 0.0;
-      for (int j = 0; j < w; j++) {
-        const int c = ptcol[j * n_C + r];
-        const double v = ptval[j * n_C + r];
-#pragma unroll
-        for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, r_loc[c + q * n_R]));
-      }
+      ell_row_sum<K, 8>(ptcol, ptval, n_C, r, w, r_loc, n_R, sum);
       const int I = cgid[r];
 #pragma unroll
       for (int q = 0; q < K; q++) {
@@ -1672,6 +1704,7 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
       }
     }
   }
+  trace_end(trace_slot < 0 ? -1 : trace_slot + 4);
   trace_end(trace_slot);
 }
 
@@ -1714,6 +1747,9 @@ void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out
   const unsigned char* pf_blob = next ? next->blob : nullptr;
   const long long* pf_off = next ? next->off : nullptr;
   const int pf_n = next ? next->n_patches : 0;
+  static const char* const kStages[4] = {".blob", ".gather", ".phases", ".tail"};
+  g_trace_sub = 4;
+  g_trace_sub_names = kStages;
   SMG_DISPATCH_K(k, {
     if (kind == PATCH_DOWN) {
       patch_set_attr<K, PATCH_DOWN>(smem);

@@ -807,6 +807,16 @@ int numeric_setup(smg_handle* h) {
   smg::Plan& pl = h->plan;
   const int nlev = static_cast<int>(h->lv.size());
   cudaStream_t st = h->stream;
+  // SMG_PRECOMPUTE_TIMING=1: stage times on stderr (synchronises after every stage)
+  static const bool timing = std::getenv("SMG_PRECOMPUTE_TIMING") != nullptr;
+  double t_stage = now_ms();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    const double t = now_ms();
+    std::fprintf(stderr, "numeric setup: %-34s %8.3f ms\n", what, t - t_stage);
+    t_stage = t;
+  };
   // LHS = A(unknown,unknown), Auk = A(unknown,known): value gathers (cpp:167,170)
   LevelDev& L0 = h->lv[0];
   smg::launch_gather_values(h->a_in.p, h->lhs_src.p, L0.a_val.p, pl.LHS.nnz(), st);
@@ -816,6 +826,7 @@ int numeric_setup(smg_handle* h) {
     smg::launch_gather_values(h->auk_csc_val.p, h->auk_pos.p, h->auk_val.p, pl.Auk.nnz(), st);
     h->launches += 2;
   }
+  lap("value gathers");
   // Galerkin products A_l = (PT * A_{l-1}) * P (cpp:25, :227)
   for (int l = 1; l < nlev; l++) {
     LevelDev& F = h->lv[l - 1];
@@ -827,6 +838,7 @@ int numeric_setup(smg_handle* h) {
                             C.p_val.p, C.t_colptr.p, C.t_rowidx.p, C.t_val.p, C.a_val.p, st);
     h->launches += 2;
   }
+  lap("Galerkin products");
   // coarsest diagonal shift (cpp:31-36, :237-242)
   LevelDev& Lc = h->lv[nlev - 1];
   smg::launch_shift_diag(Lc.a_val.p, Lc.diag_pos.p, Lc.n, 1e-12, st);
@@ -846,6 +858,7 @@ int numeric_setup(smg_handle* h) {
       }
   }
   SMG_TRY(check_launch(h, "numeric setup"));
+  lap("SELL / diagonal / patch fills");
   // coarse factorisation (cpp:46-48, :253-254): dense Cholesky, explicit inverse
   const int nc = Lc.n;
   if (nc > SMG_MAX_COARSE_ROWS)
@@ -873,6 +886,7 @@ int numeric_setup(smg_handle* h) {
     if (cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
                          h->potrf_work.p, lwork1, h->dev_info.p) != CUSOLVER_STATUS_SUCCESS)
       return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotrf failed");
+    lap("coarse: dense assembly + potrf");
     if (cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
                          h->potrf_work.p, lwork2, h->dev_info.p + 1) != CUSOLVER_STATUS_SUCCESS)
       return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotri failed");
@@ -883,6 +897,7 @@ int numeric_setup(smg_handle* h) {
       return fail(h, SMG_E_CUSOLVER,
                   "coarsest matrix is not positive definite (potrf info " +
                       std::to_string(info[0]) + ", potri info " + std::to_string(info[1]) + ")");
+    lap("coarse: potri");
     // keep only the packed lower tiles (half the bytes, contiguous 32 KB blocks)
     SMG_CUDA(h, h->ainv_tiles.reserve(smg::dense_sym_tiles_doubles(nc)));
     smg::launch_pack_sym_tiles(h->ainv.p, h->ainv_tiles.p, nc, st);
@@ -890,6 +905,7 @@ int numeric_setup(smg_handle* h) {
     SMG_TRY(check_launch(h, "coarse inverse"));
   }
   SMG_CUDA(h, cudaStreamSynchronize(st));
+  lap("coarse: tile packing");
   return SMG_OK;
 }
 
@@ -909,13 +925,19 @@ int upload_patches(smg_handle* h, int k_cols) {
   cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
   if (dev_smem <= 0 || nsm <= 0) return SMG_OK;
-  const int budget = dev_smem - 1024;  // static shared memory of the kernel + alignment slack
+  // One patch per SM (measured on B200, profiles/r2_patch_stages.md: a patch launch costs
+  // ~9 us almost independently of the patch size -- dependent chains of shared-memory loads,
+  // FP64 adds, a division and a barrier per colour phase -- so more, smaller patches only
+  // add redundant halo work and, past one wave, a second round of that latency).
+  int budget = dev_smem - 1024;
+  if (const char* e = std::getenv("SMG_PATCH_SMEM_KB")) budget = std::min(dev_smem - 1024, std::atoi(e) * 1024);
   for (int l = 0; l + 1 < nlev; l++) {
     const smg::LevelPlan& P = pl.lv[l];
     LevelDev& L = h->lv[l];
     if (P.n <= 0 || P.n > max_rows || P.layout == smg::LAYOUT_PARTITIONED) continue;
     // one patch per SM unless that makes patches too small to amortise their halo
     int target = h->opt.patch_rows > 0 ? h->opt.patch_rows : std::max(96, (P.n + nsm - 1) / nsm);
+    if (const char* e = std::getenv("SMG_PATCH_COUNT")) target = (P.n + std::max(1, std::atoi(e)) - 1) / std::max(1, std::atoi(e));
     smg::PatchSet down, up;
     std::string why;
     if (!smg::build_patches(pl, l, smg::PATCH_DOWN, h->opt.pre_relax, target, budget, k_cols, &down, &why) ||

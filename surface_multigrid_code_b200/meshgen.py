@@ -406,6 +406,32 @@ def mesh_subdivided_problem(name, V0, F0, n_sub, n_levels, known_fn=None, tol=1e
     return poisson_problem(name, V, F, P, known, tol, max_iter)
 
 
+def upsampled_mesh_problem(name: str, V0, F0, known, P_coarse, n_sub: int, tol: float = 1e-10,
+                           max_iter: int = 40, pad_three: bool = True) -> Problem:
+    """04_mg_solver_nobd/main.cpp on an input mesh upsampled ``n_sub`` times (BASELINE config 5:
+    hilbert_cube.obj x 3 = 4 028 672 vertices): unit-area normalisation of the fine mesh,
+    A = -cotmatrix, ``known`` (indices on the INPUT mesh; igl::upsample keeps them) pinned to 0,
+    b = voronoi mass, z0 = 0.  Hierarchy = the ``n_sub`` subdivision prolongations followed by
+    the given prolongations below the input mesh (``P_coarse``, fine -> coarse order)."""
+    V, F, P = subdivision_hierarchy(V0, F0, n_sub, n_sub + 1, pad_three=pad_three)
+    V = normalize_unit_area(V, F)
+    Pall = list(P)
+    for p in P_coarse:
+        p = sp.csc_matrix(p)
+        p.indices = p.indices.astype(np.int32)
+        p.indptr = p.indptr.astype(np.int32)
+        Pall.append(p)
+    return poisson_problem(name, V, F, Pall, np.asarray(known, dtype=np.int32), tol, max_iter)
+
+
+def load_csc_keep_zeros(d, key: str) -> sp.csc_matrix:
+    """CSC matrix stored as <key>_{indptr,indices,data,shape} arrays (explicit zeros kept)."""
+    shp = tuple(int(x) for x in d[f"{key}_shape"])
+    m = sp.csc_matrix(shp, dtype=np.float64)
+    m.indptr, m.indices, m.data = d[f"{key}_indptr"], d[f"{key}_indices"], d[f"{key}_data"]
+    return m
+
+
 def mcf_step_problem(V, F, P, U=None, delta: float = 0.01, tol: float = 5e-7,
                      max_iter: int = 20, L0: Optional[sp.csc_matrix] = None) -> Problem:
     """One mean-curvature-flow step of 05_example_mean_curvature_flow/main.cpp:57-79:
