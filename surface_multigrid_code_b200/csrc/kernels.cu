@@ -230,14 +230,14 @@ __device__ __forceinline__ void stage_wait(uint64_t* bar) {
 // sum[q] += sum over the row's stored entries of val * x[col + q*ldx], entries in
 // storage order, products and sums rounded separately (no FMA: the reference build has
 // none).  Gathers of a batch of kPre entries are issued together.
-template <int K, bool SKIP_DIAG, bool STAGED>
-__device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const double* x, int ldx,
-                                               double (&sum)[K]) {
-  for (int j0 = 0; j0 < rv.w; j0 += kPre) {
-    int c[kPre];
-    double xv[kPre][K];
+template <int K, bool SKIP_DIAG, bool STAGED, int PRE>
+__device__ __forceinline__ void row_accumulate_batched(const RowView& rv, int row, const double* x, int ldx,
+                                                       double (&sum)[K]) {
+  for (int j0 = 0; j0 < rv.w; j0 += PRE) {
+    int c[PRE];
+    double xv[PRE][K];
 #pragma unroll
-    for (int t = 0; t < kPre; t++)
+    for (int t = 0; t < PRE; t++)
       if (j0 + t < rv.w) {
         c[t] = STAGED ? rv.cp[(j0 + t) * 32] : ld_stream_s32(rv.cp + (j0 + t) * 32);
         if (!(SKIP_DIAG && c[t] == row)) {
@@ -250,13 +250,24 @@ __device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const
         }
       }
 #pragma unroll
-    for (int t = 0; t < kPre; t++)
+    for (int t = 0; t < PRE; t++)
       if (j0 + t < rv.w && !(SKIP_DIAG && c[t] == row)) {
         const double v = STAGED ? rv.vp[(j0 + t) * 32] : ld_stream_f64(rv.vp + (j0 + t) * 32);
 #pragma unroll
         for (int q = 0; q < K; q++) sum[q] = __dadd_rn(sum[q], __dmul_rn(v, xv[t][q]));
       }
   }
+}
+
+// Rows of the fine-level cotangent matrices hold ~7 entries (one batch of kPre); the Galerkin
+// operators of mesh-decimated hierarchies hold 15-40: their gathers go out in batches of kPreWide,
+// because every batch is one dependent round trip to L2 / DRAM.
+constexpr int kPreWide = 24;
+template <int K, bool SKIP_DIAG, bool STAGED>
+__device__ __forceinline__ void row_accumulate(const RowView& rv, int row, const double* x, int ldx,
+                                               double (&sum)[K]) {
+  if (K <= 2 && rv.w > kPre) row_accumulate_batched<K, SKIP_DIAG, STAGED, (K <= 2 ? kPreWide : kPre)>(rv, row, x, ldx, sum);
+  else row_accumulate_batched<K, SKIP_DIAG, STAGED, kPre>(rv, row, x, ldx, sum);
 }
 
 enum { MODE_SPMV = 0, MODE_RESIDUAL = 1, MODE_ADD = 2, MODE_SPMV_ZERO = 3, MODE_NORM = 4 };
@@ -774,8 +785,43 @@ void set_gs_rows(int r) {
 namespace {
 const char* const kApplyNames[5] = {"spmv", "residual", "prolong_add", "restrict_zero", "residual_norm"};
 inline size_t stage_bytes(const SellDev& M) { return static_cast<size_t>(M.max_chunk) * 12; }
+// Large levels keep the stage small (several resident CTAs per SM).  A level with at most one
+// CTA per SM may use most of the SM's shared memory: its rows can be wide (Galerkin operators of
+// decimated meshes), and without staging every batch of entries costs two dependent global
+// round trips (indices, then gathers) instead of one.
+constexpr int kStageCapSmallLevel = 200 * 1024;
+constexpr int kSmallLevelRows = 148 * kBlock;
+template <int K>
+void allow_big_stage_k() {
+  const int big = kStageCapSmallLevel;
+  cudaFuncSetAttribute(sell_apply_kernel<K, MODE_SPMV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_kernel<K, MODE_RESIDUAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_kernel<K, MODE_ADD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_apply_kernel<K, MODE_SPMV_ZERO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_spmv_ranges_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_residual_norm_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(sell_gs_phase_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+}
+void allow_big_stage() {
+  static bool done[64] = {false};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done[dev]) return;
+  allow_big_stage_k<1>();
+  allow_big_stage_k<2>();
+  allow_big_stage_k<3>();
+  allow_big_stage_k<4>();
+  done[dev] = true;
+}
 inline bool use_staged(const SellDev& M) {
-  return g_use_tma && M.max_chunk > 0 && stage_bytes(M) <= static_cast<size_t>(kStageCapBytes);
+  if (!g_use_tma || M.max_chunk <= 0) return false;
+  if (stage_bytes(M) <= static_cast<size_t>(kStageCapBytes)) return true;
+  if (M.nrows <= kSmallLevelRows && stage_bytes(M) <= static_cast<size_t>(kStageCapSmallLevel)) {
+    allow_big_stage();
+    return true;
+  }
+  return false;
 }
 
 template <int MODE>
@@ -1761,6 +1807,30 @@ void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out
                     ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n);
     }
   });
+}
+
+
+namespace {
+__global__ void solve_decide_kernel(cudaGraphConditionalHandle handle, SolveCtl* ctl, const double* norm2,
+                                    int nchunks, int in_body) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (in_body && ctl->n_his >= ctl->max_iter) {
+    cudaGraphSetConditional(handle, 0);
+    return;
+  }
+  double ss = 0.0;
+  for (int c = 0; c < nchunks; c++) ss += ld_vec(norm2 + c);
+  const double r = sqrt(ss);
+  ctl->r_his[ctl->n_his++] = r;
+  const bool finite = isfinite(r);
+  if (!finite) ctl->nonfinite = 1;
+  cudaGraphSetConditional(handle, finite && !(r < ctl->tol) ? 1u : 0u);
+}
+}  // namespace
+
+void launch_solve_decide(cudaGraphConditionalHandle handle, SolveCtl* ctl, const double* norm2, int nchunks,
+                         int in_body, cudaStream_t st) {
+  solve_decide_kernel<<<1, 32, 0, st>>>(handle, ctl, norm2, nchunks, in_body);
 }
 
 }  // namespace smg

@@ -199,4 +199,21 @@ void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out
 void launch_patch_fill(double* blob, const int* dst, const int* src, const double* csc, int64_t n,
                        cudaStream_t st);
 
+
+// ---- device-side solve loop (min_quad_with_fixed_mg.cpp:330-347 as ONE graph launch) -------
+// The residual test of every iteration runs on the device and drives a conditional WHILE node
+// of the solve graph, so a solve needs no host round trip per iteration.
+constexpr int kSolveCtlHis = 4096;  // residual measurements a device-side solve can record
+struct SolveCtl {
+  double tol;
+  int max_iter, n_his, nonfinite, pad;
+  double r_his[kSolveCtlHis];
+};
+// One thread: r = sqrt(sum of norm2[0..nchunks)), recorded in ctl->r_his; the loop goes on while
+// r is finite and not < tol.  in_body: the call sits at the end of the loop body (after a
+// V-cycle); once max_iter measurements exist it only ends the loop (the reference does not
+// measure after its last cycle).
+void launch_solve_decide(cudaGraphConditionalHandle handle, SolveCtl* ctl, const double* norm2, int nchunks,
+                         int in_body, cudaStream_t st);
+
 }  // namespace smg

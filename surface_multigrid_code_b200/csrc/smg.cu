@@ -283,6 +283,12 @@ struct smg_handle {
 
   std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
   int patch_kcols = 1;  // right-hand-side columns the patch layouts are sized for
+  // device-side solve loop: one graph per k (residual norm, test, conditional WHILE around the
+  // V-cycle); loop_state < 0: not supported here (the host loop is used)
+  std::map<int, GraphEntry> loop_graphs;
+  DevBuf<smg::SolveCtl> loop_ctl;
+  smg::SolveCtl* h_ctl = nullptr;  // pinned
+  int loop_state = 0;
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // mean-curvature-flow assembly (smg_mcf_*)
@@ -332,6 +338,9 @@ void drop_graphs(smg_handle* h) {
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   h->graphs.clear();
+  for (auto& kv : h->loop_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->loop_graphs.clear();
 }
 
 int upload_sell(smg_handle* h, const smg::Sell& S, SellBufs* out, bool need_valT) {
@@ -802,6 +811,130 @@ int residual_norm_device(smg_handle* h, int l, const double* b, const double* u,
   return SMG_OK;
 }
 
+// ---- device-side solve loop ----------------------------------------------------------
+// min_quad_with_fixed_mg.cpp:330-347 as ONE CUDA graph: [residual norm, test] followed by a
+// conditional WHILE node whose body is [V-cycle, residual norm, test].  The test kernel
+// (solve_decide_kernel) records the residual, and keeps the loop going while the residual is
+// finite and not below the tolerance and fewer than max_iter measurements exist -- the
+// reference's sequence of measurements and cycles exactly, including its last, unmeasured
+// cycle.  Used for single-GPU handles with graphs enabled; partitioned handles sum their
+// residual on the host (identical on every rank) and keep the host loop.
+void enqueue_norm(smg_handle* h, int k) {
+  LevelDev& L0 = h->lv[0];
+  const SellDev A = L0.sellA.view();
+  const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
+  for (int c = 0; c < nchunks; c++) {
+    const int k0 = c * smg::kMaxK, kk = std::min(smg::kMaxK, k - k0);
+    const size_t o = static_cast<size_t>(k0) * L0.n;
+    smg::launch_residual_norm2(A, L0.b.p + o, L0.u.p + o, L0.n, kk, h->norm_scratch.p, h->norm_counter.p,
+                               h->norm_out.p + c, h->stream);
+  }
+}
+
+int build_loop_graph(smg_handle* h, int k, GraphEntry* out) {
+  LevelDev& L0 = h->lv[0];
+  const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
+  SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
+  SMG_CUDA(h, h->norm_out.reserve(static_cast<size_t>(std::max(nchunks, 1))));
+  if (!h->loop_ctl.p) SMG_CUDA(h, h->loop_ctl.alloc(1));
+  if (!h->h_ctl) SMG_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctl), sizeof(smg::SolveCtl)));
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const int64_t before = h->launches;
+  auto bail = [&](const char* what, cudaError_t e) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(h->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+      cudaGraph_t junk = nullptr;
+      cudaStreamEndCapture(h->stream, &junk);
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    h->launches = before;
+    h->loop_state = -1;  // never tried again on this handle: the host loop is used
+    h->err = std::string("device-side solve loop unavailable (") + what + ": " + cudaGetErrorString(e) + ")";
+    return SMG_E_UNSUPPORTED;
+  };
+  cudaError_t e = cudaGraphCreate(&g, 0);
+  if (e != cudaSuccess) return bail("graph create", e);
+  cudaGraphConditionalHandle cond;
+  if ((e = cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault)) != cudaSuccess)
+    return bail("conditional handle", e);
+  // part 1: first measurement + test
+  if ((e = cudaStreamBeginCaptureToGraph(h->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) !=
+      cudaSuccess)
+    return bail("capture", e);
+  enqueue_norm(h, k);
+  smg::launch_solve_decide(cond, h->loop_ctl.p, h->norm_out.p, nchunks, 0, h->stream);
+  std::vector<cudaGraphNode_t> deps;
+  {
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* d = nullptr;
+    size_t nd = 0;
+    if ((e = cudaStreamGetCaptureInfo_v2(h->stream, &st, nullptr, nullptr, &d, &nd)) != cudaSuccess)
+      return bail("capture info", e);
+    deps.assign(d, d + nd);
+  }
+  cudaGraph_t same = nullptr;
+  if ((e = cudaStreamEndCapture(h->stream, &same)) != cudaSuccess) return bail("end capture", e);
+  // part 2: WHILE node
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = cond;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t wnode;
+  if ((e = cudaGraphAddNode(&wnode, g, deps.data(), deps.size(), &np)) != cudaSuccess) return bail("while node", e);
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  if ((e = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) !=
+      cudaSuccess)
+    return bail("body capture", e);
+  const int64_t l0 = h->launches;
+  vcycle_device(h, 0, h->opt.pre_relax, h->opt.post_relax, k);
+  enqueue_norm(h, k);
+  smg::launch_solve_decide(cond, h->loop_ctl.p, h->norm_out.p, nchunks, 1, h->stream);
+  out->launches = h->launches - l0 + nchunks + 1;  // kernels per loop iteration
+  h->launches = before;
+  if ((e = cudaStreamEndCapture(h->stream, &same)) != cudaSuccess) return bail("end body capture", e);
+  if ((e = cudaGraphInstantiate(&exec, g, 0)) != cudaSuccess) return bail("instantiate", e);
+  cudaGraphDestroy(g);
+  out->exec = exec;
+  return SMG_OK;
+}
+
+// runs the whole loop on the device; SMG_E_UNSUPPORTED: use the host loop instead
+int solve_loop_device(smg_handle* h, int k, double tol, int max_iter, double* r_his, int* nh, double* residual) {
+  if (h->loop_state < 0 || !h->opt.use_graph || dist_on(h) || max_iter < 1 || max_iter > smg::kSolveCtlHis)
+    return SMG_E_UNSUPPORTED;
+  auto it = h->loop_graphs.find(k);
+  if (it == h->loop_graphs.end()) {
+    GraphEntry ge;
+    const int rc = build_loop_graph(h, k, &ge);
+    if (rc != SMG_OK) return rc;
+    it = h->loop_graphs.emplace(k, ge).first;
+  }
+  smg::SolveCtl* hc = h->h_ctl;
+  hc->tol = tol;
+  hc->max_iter = max_iter;
+  hc->n_his = 0;
+  hc->nonfinite = 0;
+  hc->pad = 0;
+  const size_t head = offsetof(smg::SolveCtl, r_his);
+  SMG_CUDA(h, cudaMemcpyAsync(h->loop_ctl.p, hc, head, cudaMemcpyHostToDevice, h->stream));
+  SMG_CUDA(h, cudaGraphLaunch(it->second.exec, h->stream));
+  SMG_CUDA(h, cudaMemcpyAsync(hc, h->loop_ctl.p, head + sizeof(double) * max_iter, cudaMemcpyDeviceToHost, h->stream));
+  SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int n = std::max(0, std::min(hc->n_his, max_iter));
+  for (int i = 0; i < n; i++) r_his[i] = hc->r_his[i];
+  *nh = n;
+  *residual = n > 0 ? hc->r_his[n - 1] : 0.0;
+  const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
+  // cycles run: one after every measurement that did not end the loop
+  const bool ended_by_test = n > 0 && (!std::isfinite(*residual) || *residual < tol);
+  const int cycles = ended_by_test ? n - 1 : n;
+  h->launches += nchunks + 1 + static_cast<int64_t>(cycles) * it->second.launches;
+  return SMG_OK;
+}
+
 // ---- numeric part of precompute (device) -----------------------------------------
 int numeric_setup(smg_handle* h) {
   smg::Plan& pl = h->plan;
@@ -1189,17 +1322,30 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
   h->launches++;
   double residual = 0.0;
   int nh = 0;
-  for (int iter = 0; iter < max_iter; iter++) {  // cpp:330-347 / :108-125
-    SMG_TRY(residual_norm_device(h, 0, L0.b.p, L0.u.p, k, &residual));
-    r_his[nh++] = residual;
-    if (h->opt.verbose) std::printf("%.17g\n", residual);
-    if (!std::isfinite(residual)) {
+  const int rc_loop = solve_loop_device(h, k, tol, max_iter, r_his, &nh, &residual);
+  if (rc_loop == SMG_OK) {
+    if (h->opt.verbose)
+      for (int i = 0; i < nh; i++) std::printf("%.17g\n", r_his[i]);
+    if (nh > 0 && !std::isfinite(residual)) {
       *n_his = nh;
       *converged = 0;
       return fail(h, SMG_E_NONFINITE, "residual is not finite");
     }
-    if (residual < tol) break;
-    SMG_TRY(vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k));
+  } else if (rc_loop != SMG_E_UNSUPPORTED) {
+    return rc_loop;
+  } else {
+    for (int iter = 0; iter < max_iter; iter++) {  // cpp:330-347 / :108-125
+      SMG_TRY(residual_norm_device(h, 0, L0.b.p, L0.u.p, k, &residual));
+      r_his[nh++] = residual;
+      if (h->opt.verbose) std::printf("%.17g\n", residual);
+      if (!std::isfinite(residual)) {
+        *n_his = nh;
+        *converged = 0;
+        return fail(h, SMG_E_NONFINITE, "residual is not finite");
+      }
+      if (residual < tol) break;
+      SMG_TRY(vcycle_run(h, 0, h->opt.pre_relax, h->opt.post_relax, k));
+    }
   }
   if (h->opt.verbose) std::printf("residual norm: %.17g\n", residual);
   // z(unknown) = z_unknown ; z(known) = known_val   (cpp:353-355)
@@ -1322,6 +1468,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
   if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->no_prefetch = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_PATCH_ROWS")) h->opt.patch_rows = std::atoi(e);
+  if (const char* e = std::getenv("SMG_HOST_LOOP")) h->loop_state = (e[0] && e[0] != '0') ? -1 : 0;
   if (const char* e = std::getenv("SMG_NO_TMA")) smg::set_tma_enabled(!(e[0] && e[0] != '0'));
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMallocHost(reinterpret_cast<void**>(&h->h_norm), 1024 * sizeof(double)) != cudaSuccess) {
@@ -1368,6 +1515,8 @@ void smg_destroy(smg_handle* h) {
     drop_graphs(h);
     if (h->cusolver) cusolverDnDestroy(h->cusolver);
     if (h->h_norm) cudaFreeHost(h->h_norm);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    h->loop_ctl.release();
     h->lv.clear();
     // remaining DevBufs are released by the destructor below, before the stream
     h->a_in.release(); h->lhs_src.release(); h->auk_src.release(); h->g.release();

@@ -280,3 +280,28 @@ def test_launches_are_counted_and_errors_are_loud(problems):
     with pytest.raises(Exception):
         s.precompute(bad.tocsc(), pr.known)
     s.close()
+
+
+@pytest.mark.parametrize("smoother", ["wavefront", "multicolour"])
+def test_device_side_solve_loop_equals_the_host_loop(problems, smoother, monkeypatch):
+    """One smg_solve = one graph launch (residual test on the device, conditional WHILE node):
+    same r_his, return value and z as the host loop, incl. the quirks of
+    min_quad_with_fixed_mg.cpp:330-360 (no measurement after the last cycle, strict '<')."""
+    for name in ("sphere_pad", "mcf"):
+        pr = problems[name]
+        monkeypatch.delenv("SMG_HOST_LOOP", raising=False)
+        dev = Solver(smoother=smoother, device=0).set_hierarchy(pr.P).precompute(pr.A, pr.known)
+        monkeypatch.setenv("SMG_HOST_LOOP", "1")
+        host = Solver(smoother=smoother, device=0).set_hierarchy(pr.P).precompute(pr.A, pr.known)
+        monkeypatch.delenv("SMG_HOST_LOOP", raising=False)
+        for tol, max_iter in ((pr.tol, pr.max_iter), (1e-30, 4), (1e30, 5), (1e-6, 1), (1e-3, 0), (1e-9, 2)):
+            za, ra, oka = dev.solve(pr.rhs, pr.z0, pr.known_val, tol, max_iter)
+            zb, rb, okb = host.solve(pr.rhs, pr.z0, pr.known_val, tol, max_iter)
+            assert oka == okb and len(ra) == len(rb) and np.array_equal(ra, rb), (name, tol, max_iter)
+            assert np.array_equal(za, zb), (name, tol, max_iter)
+        # launches are still counted: measurements + cycles
+        c0 = dev.launch_count
+        dev.solve(pr.rhs, pr.z0, pr.known_val, 1e-30, 3)
+        assert dev.launch_count - c0 >= 3 * 6
+        dev.close()
+        host.close()
