@@ -1343,6 +1343,15 @@ void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const do
   if (nnz > 0)
     csc_to_dense_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, rowidx, colidx, val, iperm, D, n);
 }
+namespace {
+__global__ void set_identity_kernel(double* D, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) D[(size_t)i * n + i] = 1.0;
+}
+}  // namespace
+void launch_set_identity(double* D, int n, cudaStream_t st) {
+  if (n > 0) set_identity_kernel<<<blocks_for(n, 256), 256, 0, st>>>(D, n);
+}
 void launch_symmetrize_lower(double* D, int n, cudaStream_t st) {
   if (n <= 0) return;
   dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8);

@@ -145,6 +145,8 @@ void launch_csc_to_dense(int nnz, const int* rowidx, const int* colidx, const do
                          const int* iperm, double* D, int n, cudaStream_t st);
 // mirror the lower triangle of a column-major n x n matrix into the upper one
 void launch_symmetrize_lower(double* D, int n, cudaStream_t st);
+// D (n x n, zeroed) gets ones on its diagonal
+void launch_set_identity(double* D, int n, cudaStream_t st);
 // u = u + Ainv * b from the packed lower-triangular 64x64 tiles of the symmetric Ainv
 // (launch_pack_sym_tiles); scratch must hold dense_sym_scratch_doubles(n, k) doubles
 size_t dense_sym_scratch_doubles(int n, int k);

@@ -20,6 +20,7 @@
 // There is no CPU compute path in this file: without a CUDA device every compute
 // entry point fails with SMG_E_CUDA / SMG_E_STATE.
 #include <cuda_runtime.h>
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <signal.h>
 #include <unistd.h>
@@ -250,6 +251,7 @@ struct smg_handle {
   int device = -1;
   cudaStream_t stream = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
+  cublasHandle_t cublas = nullptr;
   std::string err;
 
   bool have_hierarchy = false, have_plan = false;
@@ -270,7 +272,7 @@ struct smg_handle {
   int n_known_distinct = 0;
 
   // coarse direct solve
-  DevBuf<double> ainv, ainv_tiles, coarse_scratch;
+  DevBuf<double> ainv, ainv_tiles, coarse_scratch, linv;
   DevBuf<double> potrf_work;
   DevBuf<int> dev_info;
 
@@ -1008,29 +1010,37 @@ int numeric_setup(smg_handle* h) {
     smg::launch_csc_to_dense(pl.lv[nlev - 1].A.nnz(), Lc.a_rowidx.p, Lc.a_col.p, Lc.a_val.p,
                              d_iperm.p, h->ainv.p, nc, st);
     h->launches++;
-    int lwork1 = 0, lwork2 = 0;
-    if (cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
-                                    &lwork1) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnDpotri_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
-                                    &lwork2) != CUSOLVER_STATUS_SUCCESS)
+    int lwork1 = 0;
+    if (cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc, &lwork1) !=
+        CUSOLVER_STATUS_SUCCESS)
       return fail(h, SMG_E_CUSOLVER, "cusolver bufferSize failed");
-    SMG_CUDA(h, h->potrf_work.reserve(static_cast<size_t>(std::max(lwork1, lwork2))));
+    SMG_CUDA(h, h->potrf_work.reserve(static_cast<size_t>(std::max(lwork1, 1))));
     SMG_CUDA(h, h->dev_info.reserve(2));
     if (cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
                          h->potrf_work.p, lwork1, h->dev_info.p) != CUSOLVER_STATUS_SUCCESS)
       return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotrf failed");
     lap("coarse: dense assembly + potrf");
-    if (cusolverDnDpotri(h->cusolver, CUBLAS_FILL_MODE_LOWER, nc, h->ainv.p, nc,
-                         h->potrf_work.p, lwork2, h->dev_info.p + 1) != CUSOLVER_STATUS_SUCCESS)
-      return fail(h, SMG_E_CUSOLVER, "cusolverDnDpotri failed");
-    int info[2] = {0, 0};
-    SMG_CUDA(h, cudaMemcpyAsync(info, h->dev_info.p, sizeof(info), cudaMemcpyDeviceToHost, st));
+    // explicit inverse from the Cholesky factor, A^-1 = L^-T L^-1, as two level-3 BLAS calls
+    // (X = L^-1 by a triangular solve against the identity, then X^T X): cusolverDnDpotri does
+    // the same arithmetic at a fraction of the speed (15 ms at n = 4098 on B200), and this runs
+    // once per time step of the mean-curvature flow
+    SMG_CUDA(h, h->linv.reserve(static_cast<size_t>(nc) * nc));
+    SMG_CUDA(h, cudaMemsetAsync(h->linv.p, 0, sizeof(double) * nc * nc, st));
+    smg::launch_set_identity(h->linv.p, nc, st);
+    h->launches++;
+    const double one = 1.0, zero = 0.0;
+    if (cublasDtrsm(h->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nc, nc, &one,
+                    h->ainv.p, nc, h->linv.p, nc) != CUBLAS_STATUS_SUCCESS ||
+        cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, nc, nc, &one, h->linv.p, nc, &zero, h->ainv.p,
+                    nc) != CUBLAS_STATUS_SUCCESS)
+      return fail(h, SMG_E_CUSOLVER, "cublas trsm / syrk (coarse inverse) failed");
+    int info1 = 0;
+    SMG_CUDA(h, cudaMemcpyAsync(&info1, h->dev_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SMG_CUDA(h, cudaStreamSynchronize(st));
-    if (info[0] != 0 || info[1] != 0)
+    if (info1 != 0)
       return fail(h, SMG_E_CUSOLVER,
-                  "coarsest matrix is not positive definite (potrf info " +
-                      std::to_string(info[0]) + ", potri info " + std::to_string(info[1]) + ")");
-    lap("coarse: potri");
+                  "coarsest matrix is not positive definite (potrf info " + std::to_string(info1) + ")");
+    lap("coarse: inverse (trsm + syrk)");
     // keep only the packed lower tiles (half the bytes, contiguous 32 KB blocks)
     SMG_CUDA(h, h->ainv_tiles.reserve(smg::dense_sym_tiles_doubles(nc)));
     smg::launch_pack_sym_tiles(h->ainv.p, h->ainv_tiles.p, nc, st);
@@ -1492,7 +1502,9 @@ int smg_create(smg_handle** out, const smg_options* opt) {
     tls_async = h->async_alloc;
   }
   if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS ||
-      cusolverDnSetStream(h->cusolver, h->stream) != CUSOLVER_STATUS_SUCCESS) {
+      cusolverDnSetStream(h->cusolver, h->stream) != CUSOLVER_STATUS_SUCCESS ||
+      cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS ||
+      cublasSetStream(h->cublas, h->stream) != CUBLAS_STATUS_SUCCESS) {
     smg_destroy(h);
     return SMG_E_CUSOLVER;
   }
@@ -1514,6 +1526,7 @@ void smg_destroy(smg_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     drop_graphs(h);
     if (h->cusolver) cusolverDnDestroy(h->cusolver);
+    if (h->cublas) cublasDestroy(h->cublas);
     if (h->h_norm) cudaFreeHost(h->h_norm);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     h->loop_ctl.release();
@@ -1522,7 +1535,7 @@ void smg_destroy(smg_handle* h) {
     h->a_in.release(); h->lhs_src.release(); h->auk_src.release(); h->g.release();
     h->auk_ptr.release(); h->auk_q.release(); h->auk_pos.release();
     h->auk_csc_val.release(); h->auk_val.release(); h->kidx.release(); h->ksrc.release();
-    h->ainv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
+    h->ainv.release(); h->linv.release(); h->ainv_tiles.release(); h->coarse_scratch.release(); h->potrf_work.release(); h->dev_info.release();
     h->st_a.release(); h->st_b.release(); h->st_c.release(); h->st_d.release();
     h->norm_scratch.release(); h->norm_out.release(); h->norm_counter.release(); h->flush.release();
     h->mcf.F.release(); h->mcf.vf_ptr.release(); h->mcf.vf_face.release(); h->mcf.Lval.release();
