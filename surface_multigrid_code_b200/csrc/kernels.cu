@@ -821,6 +821,12 @@ inline bool use_staged(const SellDev& M) {
     allow_big_stage();
     return true;
   }
+  // large level with wide rows (block 3n x 3n systems: ~21 entries per row): two resident CTAs
+  // per SM with their chunks staged beat more CTAs that pay two round trips per batch
+  if (M.max_width > kPre && stage_bytes(M) <= static_cast<size_t>(100 * 1024)) {
+    allow_big_stage();
+    return true;
+  }
   return false;
 }
 

@@ -287,6 +287,7 @@ bool build_patches(const Plan& pl, int l, int kind, int iters, int target_rows, 
           ent += w * (i - i0);
         }
         for (int g = C; g <= kPatchMaxColours; g++) H.grp_row[g] = n_b;
+        int passes = 0;
         for (int t = 1; t <= T; t++) {
           const int g = (t - 1) % C;
           int c = 0;
@@ -294,7 +295,9 @@ bool build_patches(const Plan& pl, int l, int kind, int iters, int target_rows, 
           H.n_active[t - 1] = static_cast<short>(c);
           ps.max_active = std::max(ps.max_active, c);
           ps.sum_updates += c;
+          passes += (c + 255) / 256;
         }
+        ps.max_passes = std::max(ps.max_passes, passes);
         int W_r = 0, W_pt = 0, W_p = 0;
         for (int f : R) W_r = std::max(W_r, cx.A.ptr[f + 1] - cx.A.ptr[f]);
         if (kind == PATCH_DOWN)
@@ -306,6 +309,7 @@ bool build_patches(const Plan& pl, int l, int kind, int iters, int target_rows, 
         H.W_p = W_p;
         for (int g = 0; g < C; g++) W_r = std::max(W_r, H.grp_w[g]);
         if (std::max(W_r, std::max(W_pt, W_p)) > 255) return fail("a row has more than 255 entries");
+        ps.max_width = std::max(ps.max_width, W_r);
         W_r = H.W_r;
         // sections: doubles first, then 4-, 2-, 1-byte arrays
         Section sec;

@@ -62,6 +62,8 @@ struct PatchSet {
   int max_blob_bytes = 0;
   int max_vec_doubles = 0;          // most (n_loc + n_b + n_R) of any patch: shared-memory vectors per column
   int max_active = 0;               // most rows updated in one phase by one patch
+  int max_passes = 0;               // most sum_t ceil(rows updated in phase t / 256) of any patch
+  int max_width = 0;                // widest stored row
   int64_t sum_own = 0, sum_loc = 0, sum_b = 0, sum_updates = 0;  // statistics
   bool empty() const { return n_patches == 0; }
 };

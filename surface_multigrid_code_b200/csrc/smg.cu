@@ -1078,14 +1078,30 @@ int upload_patches(smg_handle* h, int k_cols) {
     const smg::LevelPlan& P = pl.lv[l];
     LevelDev& L = h->lv[l];
     if (P.n <= 0 || P.n > max_rows || P.layout == smg::LAYOUT_PARTITIONED) continue;
-    // one patch per SM unless that makes patches too small to amortise their halo
-    int target = h->opt.patch_rows > 0 ? h->opt.patch_rows : std::max(96, (P.n + nsm - 1) / nsm);
+    // One patch per SM (more when the patches do not fit shared memory otherwise).
+    const bool fixed = h->opt.patch_rows > 0;
+    int target = fixed ? h->opt.patch_rows : std::max(96, (P.n + nsm - 1) / nsm);
     if (const char* e = std::getenv("SMG_PATCH_COUNT")) target = (P.n + std::max(1, std::atoi(e)) - 1) / std::max(1, std::atoi(e));
     smg::PatchSet down, up;
     std::string why;
     if (!smg::build_patches(pl, l, smg::PATCH_DOWN, h->opt.pre_relax, target, budget, k_cols, &down, &why) ||
         !smg::build_patches(pl, l, smg::PATCH_UP, h->opt.post_relax, target, budget, k_cols, &up, &why))
       continue;
+    if (!fixed && !std::getenv("SMG_PATCH_FORCE")) {
+      // Patch only where it pays (measured on B200, profiles/r2_patch_stages.md): a patch launch
+      // costs ~6 us plus ~0.6 us per colour phase and per 256 rows a patch updates in it (wide
+      // rows cost more), per wave of patches; the phase-by-phase kernels cost ~2.7 us per
+      // dependent launch.  Levels with many colours grow halos that swallow the level
+      // (hilbert_cube's decimated levels: 11-13 colours), those stay phase by phase.
+      auto cost = [&](const smg::PatchSet& ps) {
+        const double waves = std::ceil(static_cast<double>(ps.n_patches) / nsm);
+        const double wide = std::max(1.0, ps.max_width / 8.0);
+        return waves * (6.0 + 0.6 * ps.max_passes * wide * std::max(1, k_cols / 2 + k_cols % 2));
+      };
+      const int C = P.n_phases;
+      const double phase_cost = 2.7 * ((h->opt.pre_relax + h->opt.post_relax) * C + 3);
+      if (cost(down) + cost(up) > 0.85 * phase_cost) continue;
+    }
     if (std::getenv("SMG_PATCH_VERIFY")) {
       for (const smg::PatchSet* ps : {&down, &up}) {
         const std::string err = smg::verify_patches(pl, *ps);

@@ -450,6 +450,66 @@ def mcf_step_problem(V, F, P, U=None, delta: float = 0.01, tol: float = 5e-7,
     return Problem("mcf_step", A, P, None, None, rhs, z0, tol, max_iter, V, F)
 
 
+def block_prolongation(P: sp.csc_matrix) -> sp.csc_matrix:
+    """get_prolong_block (src/get_prolong.cpp:59-115): the scalar prolongation applied to each of
+    the three coordinates of a vertex, interleaved xyz: P_block(3r+d, 3c+d) = P(r, c).  Explicit
+    zeros of P stay stored entries (setFromTriplets keeps them)."""
+    P = sp.csc_matrix(P)
+    rows, cols = [], []
+    vals = []
+    coo_c = np.repeat(np.arange(P.shape[1]), np.diff(P.indptr))
+    for d in range(3):
+        rows.append(3 * P.indices.astype(np.int64) + d)
+        cols.append(3 * coo_c.astype(np.int64) + d)
+        vals.append(P.data)
+    return csc_keep_zeros(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals),
+                          (3 * P.shape[0], 3 * P.shape[1]))
+
+
+def balloon_step_problem(V, F, P, dt: float = 0.02, stiffness: float = 50.0, seed: int = 0, tol: float = 1e-8,
+                         max_iter: int = 20) -> Problem:
+    """The linear system of one Newton step of the balloon example
+    (06_example_balloon_sim/sim_utils/implicit_euler_mg_balloon.h:62-76): H = M + dt^2 K on the
+    3n interleaved-xyz degrees of freedom, free variant (no fixed values), one right-hand side,
+    zero initial guess, with the block hierarchy of mg_precompute_block.  K stands in for the
+    libshell membrane Hessian (physics out of scope): an edge-spring Hessian with the same
+    structure -- one dense SPD 3x3 block per mesh edge and vertex,
+    K_ij = -w_ij (a I + b d d^T), K_ii = -sum_j K_ij, d = unit edge direction -- so H is SPD with
+    the sparsity pattern of cotmatrix (x) ones(3, 3)."""
+    rng = np.random.default_rng(seed)
+    n = V.shape[0]
+    ij = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]], axis=0).astype(np.int64)
+    ij = np.unique(np.sort(ij, axis=1), axis=0)
+    d = V[ij[:, 1]] - V[ij[:, 0]]
+    length = np.linalg.norm(d, axis=1)
+    d = d / length[:, None]
+    w = stiffness * (1.0 + 0.3 * rng.random(ij.shape[0])) / np.maximum(length, 1e-12)
+    blocks = w[:, None, None] * (0.2 * np.eye(3)[None] + d[:, :, None] * d[:, None, :])  # SPD 3x3 per edge
+    rows, cols, vals = [], [], []
+    for a in range(3):
+        for b in range(3):
+            i3, j3 = 3 * ij[:, 0] + a, 3 * ij[:, 1] + b
+            i3b, j3b = 3 * ij[:, 0] + b, 3 * ij[:, 1] + a
+            rows += [i3, j3b, 3 * ij[:, 0] + a, 3 * ij[:, 1] + a]
+            cols += [j3, i3b, 3 * ij[:, 0] + b, 3 * ij[:, 1] + b]
+            vals += [-blocks[:, a, b], -blocks[:, a, b], blocks[:, a, b], blocks[:, a, b]]
+    K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(3 * n, 3 * n))
+    m = np.repeat(massmatrix_diag(V, F, "barycentric"), 3)
+    H = (sp.diags(m) + dt * dt * K).tocsc()
+    H.sum_duplicates()
+    H.sort_indices()
+    H.indices = H.indices.astype(np.int32)
+    H.indptr = H.indptr.astype(np.int32)
+    Pb = []
+    for p in P:
+        q = block_prolongation(p)
+        q.indices = q.indices.astype(np.int32)
+        q.indptr = q.indptr.astype(np.int32)
+        Pb.append(q)
+    g = rng.standard_normal(3 * n) * np.repeat(massmatrix_diag(V, F, "barycentric"), 3)  # -(M dq + dt G + dt f)
+    return Problem("balloon_step", H, Pb, None, None, g, np.zeros(3 * n), tol, max_iter, V, F)
+
+
 def grid_mesh(nx: int, ny: int, jitter: float = 0.0, seed: int = 0):
     """Small open (boundary-carrying) triangulated grid for unit tests."""
     xs, ys = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))

@@ -79,4 +79,8 @@ def problems():
     rng = np.random.default_rng(3)
     U = Vs * (1.0 + 0.05 * rng.standard_normal((Vs.shape[0], 1)))
     out["mcf"] = mg.mcf_step_problem(Vs, Fs, P, U=U)
+    # 06-style: block (3n x 3n, interleaved xyz) hierarchy of mg_precompute_block, free variant
+    Vb, Fb, Pb = mg.subdivision_hierarchy(V0, F0, 3, 3, project_sphere=True, pad_three=True)
+    Vb = mg.normalize_unit_area(Vb, Fb)
+    out["block"] = mg.balloon_step_problem(Vb * (1.0 + 0.1 * rng.standard_normal((Vb.shape[0], 1))), Fb, Pb)
     return out

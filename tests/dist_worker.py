@@ -34,6 +34,7 @@ def main():
     s.dist_options(halo, -1, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     s.dist_connect_torch()
     s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
+    dist.barrier()  # enter the first exchange together (a rank waits at most SMG_XCHG_TIMEOUT_MS for a peer)
     z, r_his, ok = s.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 40)
     ora = Oracle(pr.P).precompute(pr.A, pr.known)
     z_ref, r_ref, _ = ora.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 40)

@@ -41,7 +41,7 @@ def smoother_env():
         os.environ["SMG_SMOOTHER"] = old
 
 
-@pytest.mark.parametrize("name", ["sphere_pad", "grid", "mcf"])
+@pytest.mark.parametrize("name", ["sphere_pad", "grid", "mcf", "block"])
 def test_adapter_is_a_drop_in_for_the_reference_sources(problems, name, smoother_env):
     pr = problems[name]
     smoother_env(0)
@@ -82,7 +82,7 @@ def test_adapter_is_a_drop_in_for_the_reference_sources(problems, name, smoother
         assert np.linalg.norm(z1 - z2) <= 1e-9 * np.linalg.norm(z2)
 
 
-@pytest.mark.parametrize("name", ["sphere_pad", "mcf"])
+@pytest.mark.parametrize("name", ["sphere_pad", "mcf", "block"])
 def test_adapter_default_smoother_reaches_the_reference_solution(problems, name, smoother_env):
     pr = problems[name]
     smoother_env(1)

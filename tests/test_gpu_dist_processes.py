@@ -29,6 +29,9 @@ def _free_port():
 
 def _run(nproc, sub, halo, env_extra=None, timeout=420):
     env = dict(os.environ)
+    # ranks that share a GPU with each other (and with this pytest process's own context) are
+    # time-sliced: give a waiting exchange plenty of time before it declares its peer dead
+    env.setdefault("SMG_XCHG_TIMEOUT_MS", "120000")
     env.update(env_extra or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),

@@ -18,7 +18,7 @@ from surface_multigrid_code_b200.solver import Solver
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["sphere_pad", "sphere", "grid", "mcf"]
+NAMES = ["sphere_pad", "sphere", "grid", "mcf", "block"]
 
 
 def _pair(pr, smoother):

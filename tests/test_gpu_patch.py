@@ -17,7 +17,7 @@ def _pair(pr, patch_rows, **kw):
     return a, b
 
 
-@pytest.mark.parametrize("name", ["sphere_pad", "sphere", "grid", "mcf"])
+@pytest.mark.parametrize("name", ["sphere_pad", "sphere", "grid", "mcf", "block"])
 @pytest.mark.parametrize("patch_rows", [0, 40, 300])
 @pytest.mark.parametrize("graph", [True, False])
 def test_patched_vcycle_is_bit_identical_to_the_phase_kernels(problems, name, patch_rows, graph):

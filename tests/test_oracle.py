@@ -14,7 +14,7 @@ import golden_util
 from oracle.cpu_oracle import Oracle
 from scipy_restatement import Hierarchy, gauss_seidel
 
-NAMES = ["sphere_pad", "grid", "mcf"]
+NAMES = ["sphere_pad", "grid", "mcf", "block"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -151,7 +151,9 @@ def test_bench_cpu_arms_run_on_a_small_problem():
     sys.path.insert(0, root)
     import bench
 
-    pr = bench.build_problem(5, 3)
+    import argparse
+
+    pr = bench.build_problem(argparse.Namespace(workload="sphere", subdiv=5, levels=3, max_iter=20, tol=None))
     cpu = bench.cpu_baseline(pr, 3)
     assert cpu["value"] > 0 and cpu["cores"] == 1 and cpu["kind"] in ("reference", "port")
     if cpu["kind"] == "reference":

@@ -21,7 +21,7 @@ from surface_multigrid_code_b200.solver import Solver
 pytestmark = pytest.mark.skipif(not cpu_oracle.ref_available(),
                                 reason="oracle/_ref/libsmg_ref.so not built (needs /root/reference)")
 
-NAMES = ["sphere_pad", "sphere", "grid", "mcf"]
+NAMES = ["sphere_pad", "sphere", "grid", "mcf", "block"]
 
 
 def _rand(rng, n, k):
