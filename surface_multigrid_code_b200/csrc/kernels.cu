@@ -354,7 +354,13 @@ __device__ __forceinline__ void norm_finish(double d2, double* partial, unsigned
   if (!is_last) return;
   __threadfence();
   double t = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kBlock) t += ld_vec(partial + i);
+  for (int i0 = threadIdx.x; i0 < (int)gridDim.x; i0 += kBlock * 8) {  // eight loads in flight per thread
+    double v[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) v[a] = i0 + a * kBlock < (int)gridDim.x ? ld_vec(partial + i0 + a * kBlock) : 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) t += v[a];
+  }
   __shared__ double sm[kBlock];
   sm[threadIdx.x] = t;
   __syncthreads();
@@ -1212,7 +1218,14 @@ dense_sym_reduce_kernel(int trace_slot, const double* partial, double* u, int n,
   for (int q = 0; q < K; q++) {
     double sum = 0.0;
     if (i < n)
-      for (int s = g; s < nblk; s += 4) sum += ld_vec(partial + (static_cast<size_t>(s) * K + q) * n + i);
+      for (int s0 = g; s0 < nblk; s0 += 32) {  // eight loads in flight, summed in slot order
+        double v[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+          v[a] = s0 + 4 * a < nblk ? ld_vec(partial + (static_cast<size_t>(s0 + 4 * a) * K + q) * n + i) : 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; a++) sum += v[a];
+      }
     red[g][r] = sum;
     __syncthreads();
     if (g == 0 && i < n) {
@@ -1560,7 +1573,7 @@ __global__ void __launch_bounds__(kPatchThreads)
 patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long long* __restrict__ off,
              const double* u_in, double* u_out, const double* b, int ld, const double* uc, double* bc,
              double* uc_zero, int ldc, const unsigned char* __restrict__ pf_blob,
-             const long long* __restrict__ pf_off, int pf_n) {
+             const long long* __restrict__ pf_off, int pf_n, int use_tma) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bar;
   trace_begin(trace_slot);
@@ -1568,25 +1581,22 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
   pdl_launch_dependents();
   const long long o0 = off[blockIdx.x];
   const uint32_t bytes = static_cast<uint32_t>(off[blockIdx.x + 1] - o0);
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    mbar_expect_tx(&bar, bytes);
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dyn)),
-        "l"(blob + o0), "r"(bytes), "r"(smem_u32(&bar))
-        : "memory");
-  }
-  // the blobs of the NEXT patch launch of the V-cycle -> L2 (immutable data, 32 KB pieces)
-  for (int p = blockIdx.x; p < pf_n; p += gridDim.x) {
-    const long long q0 = pf_off[p], q1 = pf_off[p + 1];
-    for (long long q = q0 + 32768ll * (threadIdx.x >> 5); q < q1; q += 32768ll * (blockDim.x >> 5))
-      if ((threadIdx.x & 31) == 0) {
-        const uint32_t nb = static_cast<uint32_t>(q1 - q < 32768 ? q1 - q : 32768);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_blob + q), "r"(nb) : "memory");
-      }
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      mbar_expect_tx(&bar, bytes);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dyn)),
+          "l"(blob + o0), "r"(bytes), "r"(smem_u32(&bar))
+          : "memory");
+    }
+  } else {  // SMG_NO_TMA=1 (tools that do not model bulk copies): plain cooperative copy
+    const uint4* src = reinterpret_cast<const uint4*>(blob + o0);
+    uint4* dst = reinterpret_cast<uint4*>(dyn);
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  mbar_wait(&bar, 0);
+  if (use_tma) mbar_wait(&bar, 0);
   trace_end(trace_slot < 0 ? -1 : trace_slot + 1);  // sub-slots (tracing only): blob in shared memory
   const PatchHeader& H = *reinterpret_cast<const PatchHeader*>(dyn);
   const int n_loc = H.n_loc, n_b = H.n_b;
@@ -1765,6 +1775,17 @@ patch_kernel(int trace_slot, const unsigned char* __restrict__ blob, const long 
       }
     }
   }
+  // The blobs of the NEXT patch launch of the V-cycle -> L2 (immutable data; one 32 KB piece per
+  // thread).  Last statement of the kernel: ptxas serialises the uniform-datapath prefetch
+  // instruction over the lanes, which compute-sanitizer's synccheck misreads as divergence at
+  // any CTA barrier that follows it.
+  for (int p = blockIdx.x; p < pf_n; p += gridDim.x) {
+    const long long q0 = pf_off[p], q1 = pf_off[p + 1];
+    for (long long q = q0 + 32768ll * threadIdx.x; q < q1; q += 32768ll * blockDim.x) {
+      const uint32_t nb = static_cast<uint32_t>(q1 - q < 32768 ? q1 - q : 32768);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_blob + q), "r"(nb) : "memory");
+    }
+  }
   trace_end(trace_slot < 0 ? -1 : trace_slot + 4);
   trace_end(trace_slot);
 }
@@ -1815,11 +1836,11 @@ void launch_patch(const PatchDev& P, int kind, const double* u_in, double* u_out
     if (kind == PATCH_DOWN) {
       patch_set_attr<K, PATCH_DOWN>(smem);
       launch_kernel(name, patch_kernel<K, PATCH_DOWN>, P.n_patches, threads, smem, st, P.blob, P.off, u_in, u_out, b,
-                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n);
+                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n, g_use_tma ? 1 : 0);
     } else {
       patch_set_attr<K, PATCH_UP>(smem);
       launch_kernel(name, patch_kernel<K, PATCH_UP>, P.n_patches, threads, smem, st, P.blob, P.off, u_in, u_out, b,
-                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n);
+                    ld, uc, bc, uc_zero, ldc, pf_blob, pf_off, pf_n, g_use_tma ? 1 : 0);
     }
   });
 }
