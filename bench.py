@@ -733,7 +733,7 @@ def main():
     ap.add_argument("--no-replicas", action="store_true", help="skip the extra replica-mode measurement")
     ap.add_argument("--replicas", action="store_true",
                     help="N > 1: N independent problems instead of one row-partitioned problem")
-    ap.add_argument("--halo", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--halo", type=int, default=2, choices=[0, 1, 2],
                     help="halo exchange per sweep (0), per colour (1, = single-GPU smoother), per relax call (2)")
     ap.add_argument("--dist-levels", type=int, default=-1)
     ap.add_argument("--dist-min-rows", type=int, default=0)

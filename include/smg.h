@@ -209,8 +209,10 @@ int smg_dist_connect_files(smg_handle *h, const char *dir, const char *tag, int 
 /* exact = 1: halo exchange after every colour (the N-rank smoother is then the same
  * multicolour Gauss-Seidel as on one GPU); 0 (default): one exchange per sweep (Gauss-Seidel
  * inside a rank, Jacobi coupling across ranks); 2: one exchange per relax call (the sweeps of
- * a call see the other ranks' rows as of the start of the call).  dist_levels < 0: automatic (levels with at
- * least dist_min_rows rows per rank, default 250000; always level 0).  Before smg_precompute. */
+ * a call see the other ranks' rows as of the start of the call).  dist_levels < 0: automatic (always level 0;
+ * below it, dist_min_rows > 0: levels with at least that many rows per rank; dist_min_rows = 0: levels of at
+ * least 500 000 rows with at least 50 000 rows per rank -- smaller levels are latency-bound and their halo
+ * exchanges cost more than the split saves).  Before smg_precompute. */
 int smg_dist_set_options(smg_handle *h, int exact, int dist_levels, int dist_min_rows);
 /* out[8]: [0] rank [1] world [2] partitioned levels [3] halo exchanges issued so far
  * [4] connected [5] staging doubles per (peer, parity) slot */

@@ -702,9 +702,16 @@ int build_plan(const Csc& A, const int* known, int nknown, const std::vector<Csc
   if (pl.world > 1) {
     int nd = opt.dist_levels;
     if (nd < 0) {
+      // A level below level 0 is partitioned when that pays for its halo exchanges (~45 us per
+      // iteration, measured on B200 / NVSwitch): a colour-phase kernel costs ~2.7 us however few
+      // rows it has, so only levels of 500 000 rows or more get faster when split, whatever the
+      // number of ranks, as long as a rank keeps at least 50 000 rows.  dist_min_rows > 0
+      // replaces this rule by "at least dist_min_rows rows per rank".
       nd = 1;
       while (nd < nlev - 1 &&
-             pl.lv[nd].A.cols >= static_cast<int64_t>(opt.dist_min_rows) * pl.world)
+             (opt.dist_min_rows > 0
+                  ? pl.lv[nd].A.cols >= static_cast<int64_t>(opt.dist_min_rows) * pl.world
+                  : (pl.lv[nd].A.cols >= 500000 && pl.lv[nd].A.cols >= static_cast<int64_t>(50000) * pl.world)))
         nd++;
     }
     pl.dist_levels = std::max(1, std::min(nd, nlev - 1));

@@ -158,11 +158,12 @@ struct PlanOptions {
   int sigma = 256;
   int sort_cols = -1;  // -1: on for multicolour, off for wavefront (bit-parity order)
   // multi-GPU: number of ranks the fine levels are partitioned over, and how many levels
-  // (from level 0) are partitioned; < 0: every level with at least dist_min_rows rows per
-  // rank (always level 0, never the coarsest)
+  // (from level 0) are partitioned; < 0: automatic (always level 0, never the coarsest; below it
+  // levels of >= 500 000 rows with >= 50 000 rows per rank, or, with dist_min_rows > 0, levels
+  // with at least dist_min_rows rows per rank)
   int world = 1;
   int dist_levels = -1;
-  int dist_min_rows = 250000;
+  int dist_min_rows = 0;
 };
 
 struct Plan {

@@ -469,7 +469,8 @@ int ensure_k(smg_handle* h, int k) {
     return fail(h, SMG_E_INVALID, "more than SMG_MAX_RHS right-hand-side columns");
   if (k <= h->kcap) return SMG_OK;
   drop_graphs(h);
-  if (std::min(k, smg::kMaxK) > h->patch_kcols) {
+  if (std::min(k, smg::kMaxK) > h->patch_kcols && !dist_on(h)) {  // (partitioned handles pre-size for kMaxK
+    // columns but keep the one-column patch layout: wider solves fall back to the phase kernels there)
     // the patch layouts were sized for fewer columns per pass: lay them out again (smaller
     // patches where needed) and refill their matrix values
     bool any = false;
@@ -1095,7 +1096,10 @@ int upload_patches(smg_handle* h, int k_cols) {
       // (hilbert_cube's decimated levels: 11-13 colours), those stay phase by phase.
       auto cost = [&](const smg::PatchSet& ps) {
         const double waves = std::ceil(static_cast<double>(ps.n_patches) / nsm);
-        const double wide = std::max(1.0, ps.max_width / 8.0);
+        // rows of up to 8 entries are fetched in one batch; wider rows (Galerkin operators of
+        // decimated meshes) walk the rest entry by entry and were measured 2-3x slower per phase
+        const double w = ps.max_width / 8.0;
+        const double wide = w <= 1.0 ? 1.0 : 1.3 * w * w;
         return waves * (6.0 + 0.6 * ps.max_passes * wide * std::max(1, k_cols / 2 + k_cols % 2));
       };
       const int C = P.n_phases;
