@@ -271,9 +271,10 @@ int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
  * handles): lays out one relax call of `iters` sweeps in patches of about target_rows rows
  * (kind 0: + residual and restriction, 1: prolongation first) and, if verify != 0, proves
  * symbolically that every row update reads its neighbours at exactly the version the
- * phase-by-phase schedule would.  out[8]: [0] patches [1] owned rows [2] local rows (owned +
+ * phase-by-phase schedule would.  out[10]: [0] patches [1] owned rows [2] local rows (owned +
  * halo, summed over patches) [3] rows whose right-hand side is read [4] row updates
- * [5] largest patch blob in bytes [6] largest shared-memory vector count [7] bytes of all blobs */
+ * [5] largest patch blob in bytes [6] largest shared-memory vector count [7] bytes of all blobs
+ * [8] most passes of 256 rows over all phases of any patch [9] stored sweep entries */
 int smg_patch_plan(const smg_handle *h, int lv, int kind, int iters, int target_rows, int smem_limit,
                    int verify, int64_t *out);
 /* number of patches level lv is smoothed with on this handle (0: one kernel per colour phase) */

@@ -279,6 +279,7 @@ bool build_patches(const Plan& pl, int l, int kind, int iters, int target_rows, 
               int c = 0;
               for (int p = cx.A.ptr[v]; p < cx.A.ptr[v + 1]; p++) c += cx.A.col[p] != v;
               wrow[i] = c;
+              ps.sum_entries += c;
               w = std::max(w, c);
             }
             i++;

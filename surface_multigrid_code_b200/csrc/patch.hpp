@@ -64,7 +64,7 @@ struct PatchSet {
   int max_active = 0;               // most rows updated in one phase by one patch
   int max_passes = 0;               // most sum_t ceil(rows updated in phase t / 256) of any patch
   int max_width = 0;                // widest stored row
-  int64_t sum_own = 0, sum_loc = 0, sum_b = 0, sum_updates = 0;  // statistics
+  int64_t sum_own = 0, sum_loc = 0, sum_b = 0, sum_updates = 0, sum_entries = 0;  // statistics
   bool empty() const { return n_patches == 0; }
 };
 

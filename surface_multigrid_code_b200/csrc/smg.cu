@@ -1089,17 +1089,16 @@ int upload_patches(smg_handle* h, int k_cols) {
         !smg::build_patches(pl, l, smg::PATCH_UP, h->opt.post_relax, target, budget, k_cols, &up, &why))
       continue;
     if (!fixed && !std::getenv("SMG_PATCH_FORCE")) {
-      // Patch only where it pays (measured on B200, profiles/r2_patch_stages.md): a patch launch
-      // costs ~6 us plus ~0.6 us per colour phase and per 256 rows a patch updates in it (wide
-      // rows cost more), per wave of patches; the phase-by-phase kernels cost ~2.7 us per
-      // dependent launch.  Levels with many colours grow halos that swallow the level
-      // (hilbert_cube's decimated levels: 11-13 colours), those stay phase by phase.
+      // Patch only where it pays.  Measured on B200 (profiles/r2_patch_stages.md): a wave of
+      // patches costs ~6 us plus ~0.6 us per colour phase and per 256 rows a patch updates in it
+      // (more for the wide rows of decimated-mesh Galerkin operators: ~sqrt(mean width / 6));
+      // the phase-by-phase kernels cost ~2.7 us per dependent launch.  Levels with many colours
+      // grow halos that need several waves of small patches (hilbert_cube's 13 790-row level:
+      // 11 colours, 8 + 4 waves, 290 us against 110 us phase by phase): those stay phase by phase.
       auto cost = [&](const smg::PatchSet& ps) {
         const double waves = std::ceil(static_cast<double>(ps.n_patches) / nsm);
-        // rows of up to 8 entries are fetched in one batch; wider rows (Galerkin operators of
-        // decimated meshes) walk the rest entry by entry and were measured 2-3x slower per phase
-        const double w = ps.max_width / 8.0;
-        const double wide = w <= 1.0 ? 1.0 : 1.3 * w * w;
+        const double w = static_cast<double>(ps.sum_entries) / std::max<int64_t>(1, ps.sum_b) / 6.0;  // mean row width
+        const double wide = w <= 1.0 ? 1.0 : std::sqrt(w);
         return waves * (6.0 + 0.6 * ps.max_passes * wide * std::max(1, k_cols / 2 + k_cols % 2));
       };
       const int C = P.n_phases;
@@ -2363,6 +2362,8 @@ int smg_patch_plan(const smg_handle* h, int lv, int kind, int iters, int target_
   out[5] = ps.max_blob_bytes;
   out[6] = ps.max_vec_doubles;
   out[7] = static_cast<int64_t>(ps.blob.size());
+  out[8] = ps.max_passes;
+  out[9] = ps.sum_entries;
   return SMG_OK;
 }
 

@@ -425,10 +425,11 @@ class Solver:
     def patch_plan(self, lv: int, kind: str = "down", iters: int = 2, target_rows: int = 256,
                    smem_limit: int = 0, verify: bool = True) -> dict:
         """Lay out (and verify symbolically) the patch schedule of level lv; host only."""
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 10)()
         self._check(self._lib.smg_patch_plan(self._h, lv, {"down": 0, "up": 1}[kind], iters, target_rows,
                                              smem_limit, int(verify), out))
-        keys = ("patches", "owned", "local", "rhs_rows", "updates", "max_blob_bytes", "max_vec", "blob_bytes")
+        keys = ("patches", "owned", "local", "rhs_rows", "updates", "max_blob_bytes", "max_vec", "blob_bytes",
+                "max_passes", "entries")
         return dict(zip(keys, [int(v) for v in out]))
 
     def level_patched(self, lv: int) -> int:
