@@ -68,6 +68,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 bool g_use_pdl = true;
 bool g_use_tma = true;
 int g_gs_rows = 2;  // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2, 4)
+int g_apply2_rows = 600000;  // rows from which the residual / norm / restriction kernels take two rows per thread
 bool g_gs_attr_set = false;
 
 // ---- optional in-kernel timeline (smg_trace_*): every CTA folds %globaltimer at its
@@ -766,6 +767,7 @@ void trace_label(const char* label) { g_trace.label = label; }
 int trace_count() { return g_trace.next; }
 const char* trace_name(int i) { return g_trace.names[i].c_str(); }
 void set_tma_enabled(bool on) { g_use_tma = on; }
+void set_apply2_rows(int rows) { g_apply2_rows = rows > 0 ? rows : 600000; }
 void set_gs_rows(int r) {
   g_gs_rows = r >= 4 ? 4 : (r >= 2 ? 2 : 1);
   g_gs_attr_set = true;
@@ -852,7 +854,7 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
     return;
   }
   // large levels, k = 1: two rows per thread (fewer, fatter CTAs; see the Gauss-Seidel kernel)
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= 600000 &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= g_apply2_rows &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(span, kBlock * 2),
@@ -923,7 +925,7 @@ void launch_residual_norm2(const SellDev& M, const double* b, const double* x, i
     return;
   }
   int g = blocks_for(span, kBlock);
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= 600000 &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= g_apply2_rows &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     g = blocks_for(span, kBlock * 2);

@@ -57,6 +57,8 @@ void launch_spmv_zero(const SellDev& M, const double* x, int ldx, double* y, dou
 void set_pdl_enabled(bool on);
 // TMA (cp.async.bulk) staging of the matrix chunks in shared memory (default on)
 void set_tma_enabled(bool on);
+// rows from which the residual / norm / restriction kernels take two rows per thread (default 600000)
+void set_apply2_rows(int rows);
 // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2 or 4)
 void set_gs_rows(int r);
 // in-kernel timeline: slots of 2 x u64 [min start, max end] in nanoseconds (%globaltimer);

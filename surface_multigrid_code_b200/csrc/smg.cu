@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <signal.h>
 #include <unistd.h>
 
@@ -51,6 +52,20 @@ namespace {
 
 using smg::Csc;
 using smg::SellDev;
+
+// NVTX range (header-only NVTX 3: a no-op unless a profiler is attached) around the host-visible
+// phases of the entry points and, when the V-cycle is not replayed from a graph, around every level
+struct NvtxRange {
+  bool open = true;
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  void end() {
+    if (open) nvtxRangePop();
+    open = false;
+  }
+  ~NvtxRange() { end(); }  // (early error returns close their ranges too)
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 double now_ms() {
   using namespace std::chrono;
@@ -692,6 +707,7 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d down", l);
     smg::trace_label(label);
+    NvtxRange nvtx_level(label);
     if (use_patches(h, l, pre, post, k)) {  // :36-47 in one launch; u moves to the second buffer
       for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
         const int kk = std::min(smg::kMaxK, k - k0);
@@ -719,6 +735,7 @@ void vcycle_device(smg_handle* h, int lv0, int pre, int post, int k) {
     LevelDev& C = h->lv[l + 1];
     std::snprintf(label, sizeof(label), "L%d up", l);
     smg::trace_label(label);
+    NvtxRange nvtx_level(label);
     if (use_patches(h, l, pre, post, k)) {  // :52-56 in one launch; u returns to the first buffer
       for (int k0 = 0; k0 < k; k0 += smg::kMaxK) {
         const int kk = std::min(smg::kMaxK, k - k0);
@@ -1495,6 +1512,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   h->device = dev;
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
   if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
+  if (const char* e = std::getenv("SMG_APPLY2_ROWS")) smg::set_apply2_rows(std::atoi(e));
   if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->no_prefetch = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_PATCH_ROWS")) h->opt.patch_rows = std::atoi(e);
   if (const char* e = std::getenv("SMG_HOST_LOOP")) h->loop_state = (e[0] && e[0] != '0') ? -1 : 0;
@@ -1606,7 +1624,9 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   SMG_TRY(set_device(h));
   h->have_plan = false;
   h->mcf.ready = false;  // sized for the previous matrix
+  NvtxRange nvtx_all("smg_precompute");
   const double t0 = now_ms();
+  NvtxRange nvtx_plan("smg_precompute: host index planning");
   Csc A = make_csc(n, n, A_colptr, A_rowidx, nullptr);
   smg::PlanOptions po;
   po.smoother = h->opt.smoother;
@@ -1618,6 +1638,7 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
   if (dist_on(h) && !h->plan_only && !h->dist.connected)
     return fail(h, SMG_E_STATE, "smg_dist_connect has not been called");
   const int rc = smg::build_plan(A, known, n_known, h->P_full, po, &h->plan);
+  nvtx_plan.end();
   if (rc != SMG_OK) return fail(h, rc, h->plan.error);
   const double t1 = now_ms();
   h->timings[3] = t1 - t0;
@@ -1625,7 +1646,11 @@ int smg_precompute(smg_handle* h, int n, const int* A_colptr, const int* A_rowid
     h->have_plan = true;
     return SMG_OK;
   }
-  SMG_TRY(upload_plan(h));
+  {
+    NvtxRange r("smg_precompute: upload + patch layouts");
+    SMG_TRY(upload_plan(h));
+  }
+  NvtxRange nvtx_num("smg_precompute: numeric (Galerkin, diagonals, coarse inverse)");
   const int nnz = A_colptr[n];
   h->a_nnz = static_cast<size_t>(nnz);
   SMG_CUDA(h, h->a_in.reserve(static_cast<size_t>(nnz)));
@@ -1656,6 +1681,7 @@ int smg_update_values(smg_handle* h, const double* A_val) {
   SMG_TRY(check_ready(h, true));
   if (!A_val) return fail(h, SMG_E_INVALID, "null argument");
   SMG_TRY(set_device(h));
+  NvtxRange nvtx_all("smg_update_values");
   const double t0 = now_ms();
   const size_t nnz = h->a_nnz;  // of the last smg_precompute, not the buffer capacity
   SMG_CUDA(h, cudaMemcpyAsync(h->a_in.p, A_val, sizeof(double) * nnz, cudaMemcpyHostToDevice,
@@ -1692,7 +1718,9 @@ int smg_solve(smg_handle* h, const double* RHS, const double* known_val, const d
   const size_t cnt = static_cast<size_t>(pl.n) * k;
   const size_t nk = pl.has_fixed ? pl.known.size() : 0;
   if (nk > 0 && !known_val) return fail(h, SMG_E_INVALID, "known_val is required");
+  NvtxRange nvtx_all("smg_solve");
   const double t0 = now_ms();
+  NvtxRange nvtx_h2d("smg_solve: H2D");
   SMG_CUDA(h, h->st_a.reserve(cnt));
   SMG_CUDA(h, h->st_b.reserve(cnt));
   SMG_CUDA(h, h->st_c.reserve(cnt));
@@ -1703,12 +1731,16 @@ int smg_solve(smg_handle* h, const double* RHS, const double* known_val, const d
     SMG_CUDA(h, cudaMemcpyAsync(h->st_d.p, known_val, nk * k * sizeof(double),
                                 cudaMemcpyHostToDevice, h->stream));
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  nvtx_h2d.end();
   const double t1 = now_ms();
+  NvtxRange nvtx_loop("smg_solve: solve loop");
   const int rc = solve_core(h, h->st_a.p, nk > 0 ? h->st_d.p : nullptr, h->st_b.p, k, tol,
                             max_iter, h->st_c.p, r_his, n_his, converged);
   if (rc != SMG_OK) return rc;
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
+  nvtx_loop.end();
   const double t2 = now_ms();
+  NvtxRange nvtx_d2h("smg_solve: D2H");
   SMG_CUDA(h, cudaMemcpyAsync(z, h->st_c.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
   const double t3 = now_ms();
@@ -1764,7 +1796,9 @@ int smg_mcf_step(smg_handle* h, const double* U, double tol, int max_iter, doubl
   if (!m.ready) return fail(h, SMG_E_STATE, "smg_mcf_setup has not been called");
   if (!U || !U_out || !r_his || !n_his || !converged || max_iter < 0) return fail(h, SMG_E_INVALID, "bad argument");
   SMG_TRY(set_device(h));
+  NvtxRange nvtx_all("smg_mcf_step");
   const double t0 = now_ms();
+  NvtxRange nvtx_pre("smg_mcf_step: assembly + numeric precompute");
   const size_t cnt = static_cast<size_t>(m.nV) * 3;
   SMG_CUDA(h, cudaMemcpyAsync(m.U.p, U, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   LevelDev& L0 = h->lv[0];
@@ -1776,7 +1810,9 @@ int smg_mcf_step(smg_handle* h, const double* U, double tol, int max_iter, doubl
   h->launches += 4;
   SMG_TRY(check_launch(h, "mcf assemble"));
   SMG_TRY(numeric_setup(h));  // Galerkin products, diagonals, coarse factorisation: as smg_update_values
+  nvtx_pre.end();
   const double t1 = now_ms();
+  NvtxRange nvtx_loop("smg_mcf_step: solve loop");
   const int rc = solve_core(h, m.rhs.p, nullptr, m.U.p, 3, tol, max_iter, m.z.p, r_his, n_his, converged);
   if (rc != SMG_OK) return rc;
   SMG_CUDA(h, cudaStreamSynchronize(h->stream));
