@@ -26,6 +26,7 @@ namespace {
 
 constexpr int kBlock = 256;  // threads per CTA = 8 slices
 constexpr int kPre = 8;      // matrix entries per row prefetched into registers
+constexpr int kWide2 = 16;   // widest slice the two-rows-per-thread kernels accept (the tail beyond kPre is serial)
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------
 // Every hot-path kernel is launched with programmatic stream serialisation: it may
@@ -68,6 +69,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 bool g_use_pdl = true;
 bool g_use_tma = true;
 int g_gs_rows = 2;  // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2, 4)
+int g_multi_rows = 150000;  // rows of a colour phase from which the Gauss-Seidel kernel takes g_gs_rows rows per thread
 int g_apply2_rows = 600000;  // rows from which the residual / norm / restriction kernels take two rows per thread
 bool g_gs_attr_set = false;
 
@@ -379,7 +381,7 @@ __device__ __forceinline__ void norm_finish(double d2, double* partial, unsigned
 // entries): one row per thread makes CTAs that move only a few KB each and the kernel
 // becomes bound by CTA turnover.  Here a thread owns R rows (256 apart inside the CTA's
 // R*8 slices, staged by ONE bulk copy); all gathers of all its rows are issued before
-// the first sum.  Requires every slice to be at most W wide.
+// the first sum.  W entries per row are held in registers; wider rows finish entry by entry.
 template <int K, int MODE, int R, int W>
 __global__ void __launch_bounds__(kBlock)
 sell_apply_short_kernel(int trace_slot, int rb, int re, int nslices, int max_chunk,
@@ -450,6 +452,10 @@ sell_apply_short_kernel(int trace_slot, int rb, int re, int nslices, int max_chu
 #pragma unroll
       for (int j = 0; j < W; j++)
         if (j < w[r]) sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], xv[r][j][q]));
+      // rows wider than the register window (irregular meshes: a few slices per level): the rest
+      // entry by entry, in storage order
+      for (int j = W; j < w[r]; j++)
+        sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], ld_vec(x + scol[off[r] + j * 32] + (size_t)q * ldx)));
       const size_t o = row + (size_t)q * ldy;
       if (MODE == MODE_SPMV) y[o] = sum;
       if (MODE == MODE_ADD) y[o] = __dadd_rn(yv[r][q], sum);
@@ -503,8 +509,8 @@ sell_residual_norm_kernel(int trace_slot, int rb, int re, int nslices, int max_c
 // Gauss-Seidel phase with R rows per thread (rows 256 apart inside the CTA's R*8 slices,
 // staged by one TMA bulk copy pair): R times fewer, fatter CTAs.  A phase of a large
 // level is bound by CTA turnover (launch + set-up + one DRAM round trip per CTA), not by
-// bandwidth; this amortises it.  Phase-barrier synchronisation only; every slice must be
-// at most kPre wide.
+// bandwidth; this amortises it.  Phase-barrier synchronisation only; kPre entries per row are
+// gathered at once, wider rows (a few slices on irregular meshes) finish entry by entry.
 template <int K, int R>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_phase_multi_kernel(int trace_slot, int row0, int ps, int pe, int nslices, int max_chunk,
@@ -591,6 +597,10 @@ sell_gs_phase_multi_kernel(int trace_slot, int row0, int ps, int pe, int nslices
       for (int j = 0; j < kPre; j++)
         if (j < w[r] && scol[off[r] + j * 32] != row)
           sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], xv[r][j][q]));
+      for (int j = kPre; j < w[r]; j++) {  // rows wider than the register window, in storage order
+        const int c = scol[off[r] + j * 32];
+        if (c != row) sum = __dadd_rn(sum, __dmul_rn(sval[off[r] + j * 32], ld_vec(u + c + (size_t)q * ld)));
+      }
       u[row + (size_t)q * ld] = __ddiv_rn(__dsub_rn(bv[r][q], sum), d[r]);
     }
   }
@@ -768,6 +778,7 @@ int trace_count() { return g_trace.next; }
 const char* trace_name(int i) { return g_trace.names[i].c_str(); }
 void set_tma_enabled(bool on) { g_use_tma = on; }
 void set_apply2_rows(int rows) { g_apply2_rows = rows > 0 ? rows : 600000; }
+void set_multi_rows(int rows) { g_multi_rows = rows > 0 ? rows : 150000; }
 void set_gs_rows(int r) {
   g_gs_rows = r >= 4 ? 4 : (r >= 2 ? 2 : 1);
   g_gs_attr_set = true;
@@ -854,7 +865,7 @@ void launch_apply(const SellDev& M, const double* v, const double* x, int ldx, c
     return;
   }
   // large levels, k = 1: two rows per thread (fewer, fatter CTAs; see the Gauss-Seidel kernel)
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= g_apply2_rows &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kWide2 && span >= g_apply2_rows &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     launch_kernel(kApplyNames[MODE], sell_apply_short_kernel<1, MODE, 2, kPre>, blocks_for(span, kBlock * 2),
@@ -925,7 +936,7 @@ void launch_residual_norm2(const SellDev& M, const double* b, const double* x, i
     return;
   }
   int g = blocks_for(span, kBlock);
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre && span >= g_apply2_rows &&
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kWide2 && span >= g_apply2_rows &&
       M.max_chunk16 > 0 && static_cast<size_t>(M.max_chunk16) * 12 <= 100 * 1024) {
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     g = blocks_for(span, kBlock * 2);
@@ -980,8 +991,8 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
   if (pe <= ps) return;
   const int row0 = ps & ~31;
   // large phases: R rows per thread (fewer, fatter CTAs)
-  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kPre &&
-      pe - row0 >= 150000) {  // at least one full wave of fat CTAs
+  if (g_gs_rows > 1 && g_use_tma && k == 1 && M.max_width <= kWide2 &&
+      pe - row0 >= g_multi_rows) {  // at least one full wave of fat CTAs
     if (!g_gs_attr_set) set_gs_rows(g_gs_rows);
     const int R = g_gs_rows;
     const int mc = R == 2 ? M.max_chunk16 : M.max_chunk32s;

@@ -59,6 +59,8 @@ void set_pdl_enabled(bool on);
 void set_tma_enabled(bool on);
 // rows from which the residual / norm / restriction kernels take two rows per thread (default 600000)
 void set_apply2_rows(int rows);
+// rows of a colour phase from which the Gauss-Seidel kernel takes two rows per thread (default 150000)
+void set_multi_rows(int rows);
 // rows per thread of the Gauss-Seidel phase kernel on large phases (1, 2 or 4)
 void set_gs_rows(int r);
 // in-kernel timeline: slots of 2 x u64 [min start, max end] in nanoseconds (%globaltimer);

@@ -1513,6 +1513,7 @@ int smg_create(smg_handle** out, const smg_options* opt) {
   if (const char* e = std::getenv("SMG_NO_PDL")) smg::set_pdl_enabled(!(e[0] && e[0] != '0'));
   if (const char* e = std::getenv("SMG_GS_ROWS")) smg::set_gs_rows(std::atoi(e));
   if (const char* e = std::getenv("SMG_APPLY2_ROWS")) smg::set_apply2_rows(std::atoi(e));
+  if (const char* e = std::getenv("SMG_MULTI_ROWS")) smg::set_multi_rows(std::atoi(e));
   if (const char* e = std::getenv("SMG_NO_PREFETCH")) h->no_prefetch = (e[0] && e[0] != '0');
   if (const char* e = std::getenv("SMG_PATCH_ROWS")) h->opt.patch_rows = std::atoi(e);
   if (const char* e = std::getenv("SMG_HOST_LOOP")) h->loop_state = (e[0] && e[0] != '0') ? -1 : 0;
