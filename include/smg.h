@@ -277,6 +277,10 @@ int smg_level_stats(const smg_handle *h, int lv, int64_t *out);
  * [8] most passes of 256 rows over all phases of any patch [9] stored sweep entries */
 int smg_patch_plan(const smg_handle *h, int lv, int kind, int iters, int target_rows, int smem_limit,
                    int verify, int64_t *out);
+/* 1 if the last solve ran its loop on the device (one graph launch: conditional WHILE node around the
+ * V-cycle, residual test in solve_decide_kernel), 0 if the host drove the iterations (graphs off, ranks
+ * sharing a device, max_iter > 4096, or a driver without conditional graph nodes) */
+int smg_solve_on_device(const smg_handle *h);
 /* number of patches level lv is smoothed with on this handle (0: one kernel per colour phase) */
 int smg_level_patched(const smg_handle *h, int lv);
 

@@ -118,6 +118,7 @@ SIGNATURES = {
     "smg_level_stats": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "smg_patch_plan": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "smg_level_patched": (C.c_int, [_vp, C.c_int]),
+    "smg_solve_on_device": (C.c_int, [_vp]),
     "smg_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _ip]),
     "smg_trace_iteration": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, _dp, _dp, _ip]),
     "smg_launch_count": (C.c_int64, [_vp]),

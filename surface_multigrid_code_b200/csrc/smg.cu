@@ -256,6 +256,7 @@ struct DistBlob {  // what smg_dist_get_handle exports (smg_dist_handle_bytes() 
 struct GraphEntry {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;
+  int64_t first = 0;  // solve-loop graphs: kernels before the loop
 };
 
 }  // namespace
@@ -306,6 +307,7 @@ struct smg_handle {
   DevBuf<smg::SolveCtl> loop_ctl;
   smg::SolveCtl* h_ctl = nullptr;  // pinned
   int loop_state = 0;
+  int last_solve_on_device = 0;  // the last solve ran its loop on the device (smg_solve_on_device)
   int64_t launches = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // mean-curvature-flow assembly (smg_mcf_*)
@@ -839,15 +841,23 @@ int residual_norm_device(smg_handle* h, int l, const double* b, const double* u,
 // reference's sequence of measurements and cycles exactly, including its last, unmeasured
 // cycle.  Used for single-GPU handles with graphs enabled; partitioned handles sum their
 // residual on the host (identical on every rank) and keep the host loop.
+// partitioned level 0: every rank sums its own rows into slot `rank` of the chunk's row of
+// normv, the exchange makes every slot valid on every rank, and the test kernel adds the slots
+// in rank order: identical residuals, hence identical control flow, on all ranks
 void enqueue_norm(smg_handle* h, int k) {
   LevelDev& L0 = h->lv[0];
-  const SellDev A = L0.sellA.view();
+  DistCtx& D = h->dist;
+  const bool part = dist_on(h) && L0.layout == smg::LAYOUT_PARTITIONED;
+  const SellDev A = own_rows(h, L0, L0.sellA.view());
   const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
   for (int c = 0; c < nchunks; c++) {
     const int k0 = c * smg::kMaxK, kk = std::min(smg::kMaxK, k - k0);
     const size_t o = static_cast<size_t>(k0) * L0.n;
-    smg::launch_residual_norm2(A, L0.b.p + o, L0.u.p + o, L0.n, kk, h->norm_scratch.p, h->norm_counter.p,
-                               h->norm_out.p + c, h->stream);
+    double* out = part ? D.normv.p + static_cast<size_t>(c) * D.world + D.rank : h->norm_out.p + c;
+    smg::launch_residual_norm2(A, L0.b.p + o, L0.u.p + o, L0.n, kk, h->norm_scratch.p, h->norm_counter.p, out,
+                               h->stream);
+    h->launches++;
+    if (part) exchange(h, D.x_norm, D.normv.p + static_cast<size_t>(c) * D.world, D.world, 1);
   }
 }
 
@@ -856,6 +866,11 @@ int build_loop_graph(smg_handle* h, int k, GraphEntry* out) {
   const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
   SMG_CUDA(h, h->norm_scratch.reserve(static_cast<size_t>(smg::residual_norm_blocks(L0.n))));
   SMG_CUDA(h, h->norm_out.reserve(static_cast<size_t>(std::max(nchunks, 1))));
+  const bool part = dist_on(h) && L0.layout == smg::LAYOUT_PARTITIONED;
+  if (part) SMG_CUDA(h, h->dist.normv.reserve(static_cast<size_t>(h->dist.world) * std::max(nchunks, 16)));
+  // what the test kernel sums: the chunks' sums, or (partitioned) every rank's sum of every chunk
+  const double* norm2 = part ? h->dist.normv.p : h->norm_out.p;
+  const int n_norm2 = part ? nchunks * h->dist.world : nchunks;
   if (!h->loop_ctl.p) SMG_CUDA(h, h->loop_ctl.alloc(1));
   if (!h->h_ctl) SMG_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctl), sizeof(smg::SolveCtl)));
   cudaGraph_t g = nullptr;
@@ -883,8 +898,10 @@ int build_loop_graph(smg_handle* h, int k, GraphEntry* out) {
   if ((e = cudaStreamBeginCaptureToGraph(h->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) !=
       cudaSuccess)
     return bail("capture", e);
+  const int64_t l_first = h->launches;
   enqueue_norm(h, k);
-  smg::launch_solve_decide(cond, h->loop_ctl.p, h->norm_out.p, nchunks, 0, h->stream);
+  smg::launch_solve_decide(cond, h->loop_ctl.p, norm2, n_norm2, 0, h->stream);
+  const int64_t first_launches = h->launches - l_first + 1;
   std::vector<cudaGraphNode_t> deps;
   {
     cudaStreamCaptureStatus st;
@@ -911,8 +928,9 @@ int build_loop_graph(smg_handle* h, int k, GraphEntry* out) {
   const int64_t l0 = h->launches;
   vcycle_device(h, 0, h->opt.pre_relax, h->opt.post_relax, k);
   enqueue_norm(h, k);
-  smg::launch_solve_decide(cond, h->loop_ctl.p, h->norm_out.p, nchunks, 1, h->stream);
-  out->launches = h->launches - l0 + nchunks + 1;  // kernels per loop iteration
+  smg::launch_solve_decide(cond, h->loop_ctl.p, norm2, n_norm2, 1, h->stream);
+  out->launches = h->launches - l0 + 1;  // kernels per loop iteration
+  out->first = first_launches;           // kernels of the first measurement
   h->launches = before;
   if ((e = cudaStreamEndCapture(h->stream, &same)) != cudaSuccess) return bail("end body capture", e);
   if ((e = cudaGraphInstantiate(&exec, g, 0)) != cudaSuccess) return bail("instantiate", e);
@@ -923,7 +941,9 @@ int build_loop_graph(smg_handle* h, int k, GraphEntry* out) {
 
 // runs the whole loop on the device; SMG_E_UNSUPPORTED: use the host loop instead
 int solve_loop_device(smg_handle* h, int k, double tol, int max_iter, double* r_his, int* nh, double* residual) {
-  if (h->loop_state < 0 || !h->opt.use_graph || dist_on(h) || max_iter < 1 || max_iter > smg::kSolveCtlHis)
+  // (ranks that share a device synchronise their exchanges on the host: no graphs there)
+  if (h->loop_state < 0 || !h->opt.use_graph || (dist_on(h) && h->dist.host_group) || max_iter < 1 ||
+      max_iter > smg::kSolveCtlHis)
     return SMG_E_UNSUPPORTED;
   auto it = h->loop_graphs.find(k);
   if (it == h->loop_graphs.end()) {
@@ -947,11 +967,10 @@ int solve_loop_device(smg_handle* h, int k, double tol, int max_iter, double* r_
   for (int i = 0; i < n; i++) r_his[i] = hc->r_his[i];
   *nh = n;
   *residual = n > 0 ? hc->r_his[n - 1] : 0.0;
-  const int nchunks = (k + smg::kMaxK - 1) / smg::kMaxK;
   // cycles run: one after every measurement that did not end the loop
   const bool ended_by_test = n > 0 && (!std::isfinite(*residual) || *residual < tol);
   const int cycles = ended_by_test ? n - 1 : n;
-  h->launches += nchunks + 1 + static_cast<int64_t>(cycles) * it->second.launches;
+  h->launches += it->second.first + static_cast<int64_t>(cycles) * it->second.launches;
   return SMG_OK;
 }
 
@@ -1369,6 +1388,7 @@ int solve_core(smg_handle* h, const double* d_RHS, const double* d_kv, const dou
   double residual = 0.0;
   int nh = 0;
   const int rc_loop = solve_loop_device(h, k, tol, max_iter, r_his, &nh, &residual);
+  h->last_solve_on_device = rc_loop == SMG_OK ? 1 : 0;
   if (rc_loop == SMG_OK) {
     if (h->opt.verbose)
       for (int i = 0; i < nh; i++) std::printf("%.17g\n", r_his[i]);
@@ -2403,6 +2423,8 @@ int smg_patch_plan(const smg_handle* h, int lv, int kind, int iters, int target_
   out[9] = ps.sum_entries;
   return SMG_OK;
 }
+
+int smg_solve_on_device(const smg_handle* h) { return h ? h->last_solve_on_device : 0; }
 
 int smg_level_patched(const smg_handle* h, int lv) {
   if (!h || h->plan_only || lv < 0 || lv >= static_cast<int>(h->lv.size())) return 0;

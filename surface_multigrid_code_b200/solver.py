@@ -432,6 +432,11 @@ class Solver:
                 "max_passes", "entries")
         return dict(zip(keys, [int(v) for v in out]))
 
+    @property
+    def solved_on_device(self) -> bool:
+        """The last solve ran its loop on the device (one graph launch)."""
+        return bool(self._lib.smg_solve_on_device(self._h))
+
     def level_patched(self, lv: int) -> int:
         return int(self._lib.smg_level_patched(self._h, lv))
 

@@ -43,7 +43,8 @@ def main():
     dist.all_gather_object(zs, z.tobytes())
     same = all(b == zs[0] for b in zs)
     print(f"rank {rank}/{world} dev {dev}: ok={ok} cycles={len(r_his)} (oracle {len(r_ref)}) "
-          f"rel_err={err:.2e} identical_on_all_ranks={same} info={s.dist_info()}", flush=True)
+          f"rel_err={err:.2e} identical_on_all_ranks={same} device_loop={s.solved_on_device} info={s.dist_info()}",
+          flush=True)
     assert ok and err < 1e-7 and same
     dist.barrier()
     s.close()

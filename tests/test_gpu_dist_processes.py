@@ -44,6 +44,7 @@ def _run(nproc, sub, halo, env_extra=None, timeout=420):
     assert len(lines) == nproc, p.stdout[-2000:]
     for ln in lines:
         assert "ok=True" in ln and "identical_on_all_ranks=True" in ln, ln
+        assert "device_loop=True" in ln, ln  # one graph launch per solve on partitioned handles too
     return lines
 
 

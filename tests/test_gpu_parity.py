@@ -297,6 +297,7 @@ def test_device_side_solve_loop_equals_the_host_loop(problems, smoother, monkeyp
         for tol, max_iter in ((pr.tol, pr.max_iter), (1e-30, 4), (1e30, 5), (1e-6, 1), (1e-3, 0), (1e-9, 2)):
             za, ra, oka = dev.solve(pr.rhs, pr.z0, pr.known_val, tol, max_iter)
             zb, rb, okb = host.solve(pr.rhs, pr.z0, pr.known_val, tol, max_iter)
+            assert dev.solved_on_device == (max_iter >= 1) and not host.solved_on_device
             assert oka == okb and len(ra) == len(rb) and np.array_equal(ra, rb), (name, tol, max_iter)
             assert np.array_equal(za, zb), (name, tol, max_iter)
         # launches are still counted: measurements + cycles
