@@ -201,7 +201,11 @@ int smg_dist_connect(smg_handle *h, const void *all_blobs);
  * rank through files in `dir`, a directory every rank of the node can see (e.g.
  * /dev/shm/<job>); `tag` distinguishes rendezvous rounds inside one directory.  Rank r writes
  * dir/tag.r (temp file + rename), then polls for the other world-1 files.  Returns
- * SMG_E_INTERNAL after timeout_ms.  No CUDA involved. */
+ * SMG_E_INTERNAL after timeout_ms.  No CUDA involved.  A file carries its writer's pid and a
+ * per-process sequence number: only files of live processes are accepted (the ranks must share
+ * a pid namespace: one node, one container), every rank acknowledges what it read, and a rank
+ * removes its file once all peers have acknowledged it -- leftovers of an earlier run with the
+ * same dir / tag are never taken for a peer's blob.  Use a different tag per rendezvous round. */
 int smg_rendezvous_files(const char *dir, const char *tag, int rank, int world, const void *mine,
                          size_t bytes, void *all, int timeout_ms);
 /* smg_dist_get_handle + smg_rendezvous_files + smg_dist_connect in one call */
