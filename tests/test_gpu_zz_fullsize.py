@@ -59,3 +59,28 @@ def test_wavefront_mode_matches_the_cpu_checker_at_one_million_vertices(big):
         assert ok == ok_ref and len(r_his) == len(r_ref)
         assert np.allclose(r_his, r_ref, rtol=1e-6, atol=1e-14)
         assert rel(z, z_ref) < 1e-9
+
+
+def test_hilbert_cube_four_million_vertices():
+    """BASELINE configs[4]: hilbert_cube.obj upsampled three times (4 028 672 vertices, 346
+    nearest-vertex constraints, 6 levels; irregular valence, two decimated-style levels with
+    11-13 colours and wide rows): operator properties on every level and a solve to 1e-10 whose
+    result satisfies the system when recomputed on the host."""
+    import os
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hilbert_cube_base.npz"))
+    Pc = [mg.load_csc_keep_zeros(d, "Pc0"), mg.load_csc_keep_zeros(d, "Pc1")]
+    pr = mg.upsampled_mesh_problem("hilbert_cube", d["V"], d["F"], d["known"], Pc, 3, tol=1e-10, max_iter=40)
+    assert pr.n == 4028672 and pr.nlev == 6 and pr.known.size == 346
+    with Solver(device=0) as s:
+        s.set_hierarchy(pr.P).precompute(pr.A, pr.known)
+        assert s.level_rows(0) == pr.n - 346
+        pc.check_operator_properties(s, pr.nlev, np.random.default_rng(11), tol=1e-10)
+        z, r_his, ok = s.solve(pr.rhs, pr.z0, pr.known_val, 1e-10, 40)
+        assert ok and r_his[-1] < 1e-10 and len(r_his) <= 30
+        assert np.all(np.diff(r_his[2:]) < 0)  # monotone after the first cycles
+        A = pr.A.tocsr()
+        unknown = np.setdiff1d(np.arange(pr.n), pr.known)
+        assert np.linalg.norm((pr.rhs - A @ z)[unknown]) < 1e-9
+        assert np.array_equal(z[pr.known], pr.known_val)
+        assert s.solved_on_device
