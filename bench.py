@@ -333,7 +333,7 @@ def run_gpu(args):
     # through peer-mapped memory inside the V-cycle graph); --replicas: N independent problems
     partitioned = world > 1 and not args.replicas
     if partitioned:
-        # staging: every rank receives up to n/world rows x 4 columns as 16-byte words from
+        # staging: every rank receives up to n/world rows x 4 columns at 16 bytes per value from
         # every peer, double-buffered
         comm_mb = args.comm_mb or max(256, (pr.n * 4 * 16 * 2 * 5 // 4 >> 20) + 16)
         s.dist_init(rank, world, comm_mb << 20)

@@ -47,7 +47,8 @@ typedef enum smg_status {
   SMG_E_NCCL = 7,
   SMG_E_NOT_SYMMETRIC = 8, /* sparsity pattern of A is not symmetric */
   SMG_E_UNSUPPORTED = 9,
-  SMG_E_INTERNAL = 10      /* a device-side wait timed out (dataflow smoother); results are invalid */
+  SMG_E_INTERNAL = 10      /* a device-side wait timed out (halo exchange: a peer rank died) or an internal check
+                              failed; results are invalid */
 } smg_status;
 
 typedef enum smg_smoother {

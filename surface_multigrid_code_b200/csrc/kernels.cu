@@ -1251,7 +1251,7 @@ dense_sym_reduce_kernel(int trace_slot, const double* partial, double* u, int n,
 }
 
 // pack the lower-triangular 64x64 tiles of a symmetric matrix whose LOWER triangle is valid
-// (cusolver potri output) into contiguous tiles, mirroring inside the diagonal tiles
+// (the output of syrk / potri) into contiguous tiles, mirroring inside the diagonal tiles
 __global__ void __launch_bounds__(256)
 pack_sym_tiles_kernel(const double* __restrict__ A, double* __restrict__ tiles, int n) {
   const int t = blockIdx.x;

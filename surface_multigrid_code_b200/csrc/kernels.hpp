@@ -92,10 +92,11 @@ void launch_gs_phase(const SellDev& M, const double* diag, const double* b, doub
                      int k, int ps, int pe, const GsFlow& flow, cudaStream_t st);
 
 // ---- multi-GPU halo exchange over peer-mapped memory ------------------------------------
-// One (exchange, peer) pair.  The sender gathers vec[send_idx[i]] and stores {value, epoch}
-// as one 16-byte word into the PEER's staging slot (a store over NVLink); the receiver polls
-// the words of its own slot until the epoch matches and scatters them into vec[recv_idx[i]].
-// A slot therefore holds (k * n + 1) 16-byte words (the last one is the per-pair sync word).
+// One (exchange, peer) pair.  The sender gathers vec[send_idx[i]] and stores it as two 8-byte
+// words {half of the value, epoch} into the PEER's staging slot (stores over NVLink); the receiver
+// polls the words of its own slot until both carry the epoch and scatters the values into
+// vec[recv_idx[i]].  A slot therefore holds (k * n + 1) pairs of words (16 bytes per value; the
+// last pair is the per-pair sync word).
 // Staging is double-buffered by epoch parity: a rank can be at most one exchange ahead of
 // a peer, because it cannot leave exchange e before the peer has entered it.
 struct XchgPeer {

@@ -396,7 +396,7 @@ int build_exchange(smg_handle* h, const smg::Exchange& X, ExchDev* out) {
     out->any = false;
     return SMG_OK;
   }
-  if ((X.max_count() * smg::kMaxK + 1) * 2 > D.slot_doubles)  // 16-byte words, + the sync word
+  if ((X.max_count() * smg::kMaxK + 1) * 2 > D.slot_doubles)  // 16 bytes per value, + the sync word
     return fail(h, SMG_E_INVALID,
                 "halo exchange of " + std::to_string(X.max_count()) + " rows does not fit the comm buffer; "
                 "raise smg_dist_init's comm_bytes");
