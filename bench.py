@@ -575,7 +575,8 @@ def run_gpu(args):
                 "rows_per_level": [st["rows"] for st in stats],
                 "precompute_s": t_pre}),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(8 * (2 * n * k + h_kv.numel())) * world,
+                    # (partitioned: every rank copies 1/N of the rows of RHS / z0, NVLink completes them)
+                    "h2d_bytes_per_step": int(8 * 2 * n * k) * (1 if partitioned else world) + int(8 * h_kv.numel()) * world,
                     "d2h_bytes_per_step": int(8 * n * k + 8 * (cycles_per_solve + 1)) * world,
                     "step": f"one smg_solve call = {cycles_per_solve} V-cycles to tol {pr.tol}",
                     "ms_per_solve": e2e_ms_max / n_solves, "solves": n_solves},

@@ -205,6 +205,8 @@ struct DistCtx {
   DevBuf<int> ctrl;
   DevBuf<double> normv;
   ExchDev x_norm;
+  ExchDev x_slices;  // rows [slice_b(s), slice_b(s+1)) of the caller's n-vectors: rank s -> everybody (sharded H2D)
+  bool slices_ok = false;
   int64_t exchanges = 0;
   bool shared_device = false;  // some other rank uses this device too (tests): late PDL trigger
   std::shared_ptr<HostGroup> host_group;  // non-null: host-synchronised exchanges (see HostGroup)
@@ -473,6 +475,25 @@ int upload_dist(smg_handle* h) {
       for (int d = 0; d < D.world; d++)
         if (s != d) X.idx[static_cast<size_t>(s) * D.world + d] = {s};
     SMG_TRY(build_exchange(h, X, &D.x_norm));
+    // Sharded host-to-device copies of smg_solve: rank s copies only rows [n s / W, n (s + 1) / W)
+    // of the caller's RHS / z0 over PCIe and the ranks complete each other's copies over
+    // NVLink.  Optional: without room in the comm buffer every rank copies everything.
+    D.slices_ok = false;
+    const int n = h->plan.n, W = D.world;
+    const size_t per = static_cast<size_t>((n + W - 1) / W);
+    if (!D.host_group && (per * smg::kMaxK + 1) * 2 <= D.slot_doubles) {
+      smg::Exchange S;
+      S.idx.assign(static_cast<size_t>(W) * W, {});
+      for (int src = 0; src < W; src++) {
+        const int b = static_cast<int>(static_cast<int64_t>(n) * src / W), e = static_cast<int>(static_cast<int64_t>(n) * (src + 1) / W);
+        std::vector<int> rows(static_cast<size_t>(e - b));
+        std::iota(rows.begin(), rows.end(), b);
+        for (int d = 0; d < W; d++)
+          if (d != src) S.idx[static_cast<size_t>(src) * W + d] = rows;
+      }
+      SMG_TRY(build_exchange(h, S, &D.x_slices));
+      D.slices_ok = D.x_slices.any;
+    }
   }
   return SMG_OK;
 }
@@ -1599,7 +1620,7 @@ void smg_destroy(smg_handle* h) {
     h->mcf.F.release(); h->mcf.vf_ptr.release(); h->mcf.vf_face.release(); h->mcf.Lval.release();
     h->mcf.dblA.release(); h->mcf.mass.release(); h->mcf.U.release(); h->mcf.rhs.release(); h->mcf.z.release();
     DistCtx& D = h->dist;
-    D.ctrl.release(); D.normv.release(); D.x_norm = ExchDev();
+    D.ctrl.release(); D.normv.release(); D.x_norm = ExchDev(); D.x_slices = ExchDev();
     for (size_t q = 0; q < D.peer.size(); q++)
       if (D.opened[q] && D.peer[q]) cudaIpcCloseMemHandle(D.peer[q]);
     if (h->stream) cudaStreamSynchronize(h->stream);  // the frees above are stream-ordered
@@ -1746,8 +1767,21 @@ int smg_solve(smg_handle* h, const double* RHS, const double* known_val, const d
   SMG_CUDA(h, h->st_b.reserve(cnt));
   SMG_CUDA(h, h->st_c.reserve(cnt));
   SMG_CUDA(h, h->st_d.reserve(nk * k));
-  SMG_CUDA(h, cudaMemcpyAsync(h->st_a.p, RHS, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  SMG_CUDA(h, cudaMemcpyAsync(h->st_b.p, z0, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (dist_on(h) && h->dist.slices_ok) {
+    // every rank copies its slice of the rows (per column), the exchange completes the vectors
+    const int W = h->dist.world, me = h->dist.rank;
+    const size_t b = static_cast<size_t>(static_cast<int64_t>(pl.n) * me / W), e = static_cast<size_t>(static_cast<int64_t>(pl.n) * (me + 1) / W);
+    for (int q = 0; q < k && e > b; q++) {
+      const size_t o = static_cast<size_t>(q) * pl.n + b;
+      SMG_CUDA(h, cudaMemcpyAsync(h->st_a.p + o, RHS + o, (e - b) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      SMG_CUDA(h, cudaMemcpyAsync(h->st_b.p + o, z0 + o, (e - b) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    exchange(h, h->dist.x_slices, h->st_a.p, pl.n, k);
+    exchange(h, h->dist.x_slices, h->st_b.p, pl.n, k);
+  } else {
+    SMG_CUDA(h, cudaMemcpyAsync(h->st_a.p, RHS, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SMG_CUDA(h, cudaMemcpyAsync(h->st_b.p, z0, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   if (nk > 0)
     SMG_CUDA(h, cudaMemcpyAsync(h->st_d.p, known_val, nk * k * sizeof(double),
                                 cudaMemcpyHostToDevice, h->stream));
